@@ -1,0 +1,213 @@
+/* turbo_b200.h — C ABI of the B200-native dive-and-solve engine.
+ *
+ * This is the drop-in boundary for Turbo's hot path.  The reference has no
+ * FFI: its seam is the C++ template boundary between the host driver and the lattice-land
+ * device templates.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions: caller owns all host buffers; the library owns device memory; status codes, no
+ * exceptions, no callbacks; plain pointers and sizes only.  All integers are int32 unless noted;
+ * bounds use TB_NEG_INF / TB_POS_INF as the -oo / +oo sentinels (reference: Itv = Interval<ZLB<int>>
+ * with TURBO_ITV_BITS=32, include/common_solving.hpp:41-54).
+ */
+#ifndef TURBO_B200_H
+#define TURBO_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_NEG_INF INT32_MIN
+#define TB_POS_INF INT32_MAX
+
+/* Operator of a ternary-normal-form propagator  x = y op z.
+ * Replaces lala::Sig inside PIR's bytecode_type {op,x,y,z}
+ * (include/common_solving.hpp:738-771, include/barebones_dive_and_solve.hpp:82). */
+typedef enum {
+  TB_OP_ADD  = 0,  /* x = y + z                                   */
+  TB_OP_MUL  = 1,  /* x = y * z                                   */
+  TB_OP_TDIV = 2,  /* x = y / z, truncated, z != 0 (int_div)      */
+  TB_OP_TMOD = 3,  /* x = y mod z, truncated remainder (int_mod)  */
+  TB_OP_MIN  = 4,  /* x = min(y, z)                               */
+  TB_OP_MAX  = 5,  /* x = max(y, z)                               */
+  TB_OP_EQ   = 6,  /* x = (y == z), x in 0..1                     */
+  TB_OP_LEQ  = 7,  /* x = (y <= z), x in 0..1                     */
+  TB_NUM_OPS = 8
+} tb_op;
+
+/* One propagator, 16 bytes, immutable (bytecode_type, barebones_dive_and_solve.hpp:561). */
+typedef struct { int32_t op, x, y, z; } tb_prop;
+
+/* Variable / value orders (lala::VariableOrder / ValueOrder as used in
+ * barebones_dive_and_solve.hpp:193-221 and :362-387). */
+typedef enum { TB_VAR_INPUT_ORDER = 0, TB_VAR_FIRST_FAIL = 1, TB_VAR_ANTI_FIRST_FAIL = 2,
+               TB_VAR_SMALLEST = 3, TB_VAR_LARGEST = 4 } tb_var_order;
+typedef enum { TB_VAL_MIN = 0, TB_VAL_MAX = 1, TB_VAL_SPLIT = 2, TB_VAL_REVERSE_SPLIT = 3 } tb_val_order;
+
+/* One search strategy (StrategyType, barebones_dive_and_solve.hpp:84); n == 0 means "all store
+ * variables" (:242,284). */
+typedef struct { int32_t var_order, val_order, n; const int32_t* vars; } tb_strategy;
+
+/* The root problem: what UnifiedData::root + GridData carry across the launch boundary
+ * (barebones_dive_and_solve.hpp:57-78, 409-453). Host-owned, read-only to the library. */
+typedef struct {
+  int32_t nvars, nprops;
+  const int32_t* lb;              /* [nvars] */
+  const int32_t* ub;              /* [nvars] */
+  const tb_prop* props;           /* [nprops] */
+  int32_t nstrategies;
+  const tb_strategy* strategies;
+  int32_t has_eps_strategy;       /* GridData::has_eps_strategy (:434) */
+  int32_t obj_var;                /* -1 = satisfaction; always minimised (:439-443) */
+} tb_problem;
+
+typedef enum { TB_FP_AC1 = 0, TB_FP_WAC1 = 1 } tb_fixpoint_kind;
+
+/* Store placement (MemoryKind, include/memory_gpu.hpp:18-22) plus the B200 cluster/DSMEM tier. */
+typedef enum { TB_MEM_AUTO = -1, TB_MEM_GLOBAL = 0, TB_MEM_STORE_SHARED = 1, TB_MEM_TCN_SHARED = 2,
+               TB_MEM_STORE_CLUSTER = 3 } tb_mem_kind;
+
+/* The subset of Configuration<> read on the device or by configure_gpu_barebones
+ * (include/config.hpp:32-57, barebones_dive_and_solve.hpp:527-606). 0 means "auto" unless noted. */
+typedef struct {
+  int32_t fixpoint;             /* tb_fixpoint_kind; -fp */
+  int32_t wac1_threshold;       /* -wac1_threshold */
+  int32_t subproblems_power;    /* -sub; -1 = auto: smallest d with 2^d >= factor * blocks * gpus */
+  int32_t subproblems_factor;   /* -subfactor (reference default 300) */
+  int32_t or_blocks;            /* -or / -p; 0 = auto */
+  int32_t threads_per_block;    /* 0 = auto (reference compiles 256) */
+  int32_t mem_kind;             /* tb_mem_kind; TB_MEM_AUTO = placement policy; -globalmem forces GLOBAL */
+  int32_t cluster_size;         /* CTAs per cluster for STORE_CLUSTER; 0 = auto */
+  int32_t verbose;              /* -v count */
+  int32_t max_depth;            /* decision stack capacity; 0 = 10000 (MAX_SEARCH_DEPTH, :14) */
+  int32_t gpu_rank, gpu_world;  /* subproblem shard of this solver: idx = k * world + rank; 0/0 or 0/1 = all */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t reserved;
+  uint64_t timeout_ms;          /* -t; 0 = none (enforced by the caller through stop_flag and here) */
+  uint64_t cutnodes;            /* -cutnodes; 0 = none (per block, barebones :1024) */
+  uint64_t seed;
+} tb_options;
+
+enum { TB_TIMER_OVERALL = 0, TB_TIMER_PREPROCESSING, TB_TIMER_SEARCH, TB_TIMER_FIXPOINT,
+       TB_TIMER_TRANSFER_CPU2GPU, TB_TIMER_TRANSFER_GPU2CPU, TB_TIMER_SELECT_FP_FUNCTIONS,
+       TB_TIMER_WAIT_CPU, TB_TIMER_DIVE, TB_TIMER_LATEST_BEST_OBJ_FOUND, TB_TIMER_FIRST_BLOCK_IDLE,
+       TB_NUM_TIMERS };
+
+/* Every counter and timer of Statistics<> (include/statistics.hpp:137-154, Timer :13-29). */
+typedef struct {
+  int32_t num_blocks, depth_max, exhaustive, threads_per_block;
+  int32_t mem_kind, cluster_size, subproblems_power, blocks_per_sm;
+  uint64_t nodes, fails, solutions;
+  uint64_t eps_num_subproblems, eps_solved_subproblems, eps_skipped_subproblems, num_blocks_done;
+  uint64_t fixpoint_iterations, num_deductions;
+  uint64_t bounds_narrowed;       /* successful lb/ub updates (4 B each in the roofline) */
+  uint64_t shared_bytes, store_bytes, prop_bytes;   /* memory_gpu.hpp:113-122 */
+  int64_t cumulative_time_block_ns;
+  int64_t timers_ns[TB_NUM_TIMERS];
+  double kernel_ms;               /* device time of the solve kernel (CUDA events on its stream) */
+} tb_stats;
+
+typedef enum { TB_OK = 0, TB_ERR_INVALID = 1, TB_ERR_CUDA = 2, TB_ERR_NOMEM = 3, TB_ERR_UNSUPPORTED = 4,
+               TB_ERR_NO_DEVICE = 5, TB_ERR_IO = 6, TB_ERR_PARSE = 7, TB_ERR_DEPTH = 8 } tb_status;
+
+typedef struct tb_solver tb_solver;
+
+/* ---- engine ------------------------------------------------------------------------------------ */
+
+/* Copies the problem to the device, chooses blocks / subproblem depth / placement.
+ * Replaces configure_gpu_barebones + UnifiedData construction + initialize_global_data
+ * (barebones_dive_and_solve.hpp:479-483, 527-613). */
+tb_status tb_create(tb_solver** out, const tb_problem* problem, const tb_options* options);
+
+/* One fixpoint of all propagators on a caller-supplied store (NULL lb_in/ub_in = the root store).
+ * Parity hook for `propagate()`'s fixpoint + PIR::deduce (barebones_dive_and_solve.hpp:903-966).
+ * On failure (*failed = 1) the output store contents are not canonical. */
+tb_status tb_propagate(tb_solver*, const int32_t* lb_in, const int32_t* ub_in,
+                       int32_t* lb_out, int32_t* ub_out, int32_t* failed, tb_stats* stats);
+
+/* Batched form: nstores independent stores, one block (or cluster) each, laid out [nstores][nvars].
+ * This is the throughput-measurement entry for the fixpoint kernel. */
+tb_status tb_propagate_batch(tb_solver*, int32_t nstores, const int32_t* lb_in, const int32_t* ub_in,
+                             int32_t* lb_out, int32_t* ub_out, int32_t* failed, tb_stats* stats);
+
+/* The EPS dive to subproblem `idx` at depth `depth` (barebones_dive_and_solve.hpp:663-741).
+ * Outputs the store at the subproblem root *before* its first solve-propagation,
+ * the remaining depth when a leaf was hit early (0 when the subproblem was reached), and whether
+ * that leaf was a failure (1), a solution (2) or none (0). */
+tb_status tb_dive(tb_solver*, uint64_t subproblem_idx, int32_t depth,
+                  int32_t* lb_out, int32_t* ub_out, int32_t* remaining_depth, int32_t* leaf_kind);
+
+/* Batched dive: subproblems [first, first+count), outputs laid out [count][nvars]. */
+tb_status tb_dive_batch(tb_solver*, uint64_t first, int32_t count, int32_t depth,
+                        int32_t* lb_out, int32_t* ub_out, int32_t* remaining_depth, int32_t* leaf_kind);
+
+/* The whole dive-and-solve run: persistent kernel, host poll on *stop_flag / timeout, reduction.
+ * Replaces gpu_barebones_solve + wait_solving_ends + reduce_blocks
+ * (barebones_dive_and_solve.hpp:487-497, 620-901, 1033-1067; memory_gpu.hpp:174-196).
+ * Blocks until done; safe to interrupt by writing *stop_flag != 0 from a signal handler/thread. */
+tb_status tb_solve(tb_solver*, volatile int32_t* stop_flag,
+                   int32_t* best_lb, int32_t* best_ub, int32_t* has_solution,
+                   int32_t* exhaustive, tb_stats* stats);
+
+/* Cross-GPU incumbent sharing.  Each solver owns one device int32 incumbent cell.
+ * Same process: link solvers living on different devices (peer access is enabled here).
+ * Other processes (one rank per GPU): export a 64-byte CUDA IPC handle and import the peers'. */
+tb_status tb_link_peers(tb_solver** solvers, int32_t n);
+tb_status tb_export_bound_handle(tb_solver*, void* handle64);
+tb_status tb_import_peer_bounds(tb_solver*, const void* handles64, int32_t npeers);
+/* Current value of this solver's incumbent cell (TB_POS_INF when none). */
+tb_status tb_read_bound(tb_solver*, int32_t* bound);
+
+/* Fills `stats` with the launch configuration chosen by tb_create (num_blocks, mem_kind, ...). */
+tb_status tb_get_config(tb_solver*, tb_stats* stats);
+
+void tb_destroy(tb_solver*);
+const char* tb_last_error(void);
+const char* tb_version(void);
+/* Number of visible CUDA devices, or 0. Never fails. */
+int32_t tb_device_count(void);
+
+/* ---- host front-end (C++ behind a C surface) ------------------------------------------------- */
+
+typedef struct tb_model tb_model;
+
+/* FlatZinc -> TNF.  Replaces parse_flatzinc + ternarize/normalize + interpret
+ * (include/common_solving.hpp:404-439, 520-585). flags: bit0 = disable simplification. */
+tb_status tb_model_load_fzn(tb_model** out, const char* path, uint32_t flags);
+/* Same from a memory buffer (text need not be NUL-terminated). */
+tb_status tb_model_parse_fzn(tb_model** out, const char* text, size_t len, uint32_t flags);
+/* Synthetic random TNF network with a planted solution. */
+tb_status tb_model_synthetic(tb_model** out, int32_t nvars, int32_t nprops, uint64_t seed);
+/* Load / save the compact binary TNF (tests/golden fixtures). */
+tb_status tb_model_load_tnf(tb_model** out, const char* path);
+tb_status tb_model_save_tnf(const tb_model*, const char* path);
+
+const tb_problem* tb_model_problem(const tb_model*);
+/* 1 when the FlatZinc model maximises (the TNF minimises __MINIMIZE_OBJ = -x, common_solving.hpp:489-510),
+ * 0 minimise, -1 satisfy. */
+int32_t tb_model_objective_kind(const tb_model*);
+/* TNF variable holding the user's objective (not the negated one), or -1. */
+int32_t tb_model_user_objective_var(const tb_model*);
+int32_t tb_model_num_parsed_variables(const tb_model*);
+int32_t tb_model_num_parsed_constraints(const tb_model*);
+/* Root store was found inconsistent while building / preprocessing. */
+int32_t tb_model_root_failed(const tb_model*);
+
+/* Re-check a point (value of var v = lb[v]) against the ORIGINAL FlatZinc constraints; returns the
+ * number of violated constraints (0 = valid) or -1 when the model carries no FlatZinc source
+ * (synthetic / .tnf models: use tb_model_check_tnf). */
+int32_t tb_model_check_solution(const tb_model*, const int32_t* lb, const int32_t* ub);
+/* Check every TNF propagator at the point lb[]. Returns the number violated. */
+int32_t tb_model_check_tnf(const tb_model*, const int32_t* lb);
+/* Print the solution in FlatZinc output syntax (SolverOutput::print_solution,
+ * common_solving.hpp:847-851) into buf; returns bytes needed (excluding NUL). */
+size_t tb_model_format_solution(const tb_model*, const int32_t* lb, const int32_t* ub, char* buf, size_t cap);
+void tb_model_destroy(tb_model*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURBO_B200_H */
