@@ -1,0 +1,180 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle, bit for bit.
+
+Everything here needs a B200; nothing reads /root/reference.
+"""
+import numpy as np
+import pytest
+
+from tests import tnf_gen
+from turbo_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [abi.MEM_TCN_SHARED, abi.MEM_STORE_SHARED, abi.MEM_GLOBAL]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from turbo_b200 import engine
+    assert engine.device_count() > 0, "no CUDA device: the engine has no CPU fallback"
+    return engine
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle_py
+    return oracle_py
+
+
+def assert_same_store(g, o, what):
+    assert g["failed"] == o["failed"], what
+    if not o["failed"]:
+        bad = np.nonzero((g["lb"] != o["lb"]) | (g["ub"] != o["ub"]))[0]
+        assert len(bad) == 0, (what, bad[:5], g["lb"][bad[:5]], o["lb"][bad[:5]], g["ub"][bad[:5]], o["ub"][bad[:5]])
+
+
+@pytest.mark.parametrize("fp", [abi.FP_AC1, abi.FP_WAC1])
+@pytest.mark.parametrize("kind", KINDS)
+def test_root_fixpoint_bit_exact(eng, orc, kind, fp):
+    for seed, (nv, npr) in enumerate([(8, 5), (33, 64), (100, 300), (1000, 3000), (5000, 20000), (20000, 6000)]):
+        pb = tnf_gen.planted(nv, npr, seed)
+        if kind == abi.MEM_TCN_SHARED and pb.nvars * 8 + pb.nprops * 8 > 200_000:
+            continue
+        o = orc.fixpoint(pb)
+        with eng.Solver(pb, mem_kind=kind, fixpoint=fp) as s:
+            assert s.config()["mem_kind"] == kind
+            g = s.propagate()
+        assert_same_store(g, o, (kind, fp, nv, npr))
+        assert g["stats"]["num_deductions"] > 0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_failed_and_unsat_stores(eng, orc, kind):
+    # no planted solution: many of these fail at the root; the failure flag must agree
+    nfailed = 0
+    for seed in range(30):
+        pb = tnf_gen.random_net(20, 40, 500 + seed, lo=-5, hi=5)
+        o = orc.fixpoint(pb)
+        with eng.Solver(pb, mem_kind=kind) as s:
+            g = s.propagate()
+        assert_same_store(g, o, (kind, seed))
+        nfailed += o["failed"]
+    assert nfailed > 0
+
+
+def test_batch_of_perturbed_stores(eng, orc):
+    pb = tnf_gen.planted(400, 1200, 3)
+    rng = np.random.default_rng(0)
+    B = 64
+    lb = np.tile(pb.lb, (B, 1))
+    ub = np.tile(pb.ub, (B, 1))
+    for b in range(B):          # random extra narrowing, sometimes inconsistent
+        vs = rng.integers(3, pb.nvars, size=8)
+        for v in vs:
+            m = int(rng.integers(pb.lb[v], pb.ub[v] + 1))
+            if rng.random() < 0.5:
+                lb[b, v] = m
+            else:
+                ub[b, v] = m
+    with eng.Solver(pb) as s:
+        g = s.propagate_batch(lb, ub)
+    for b in range(B):
+        o = orc.fixpoint(pb, lb[b], ub[b])
+        assert_same_store(dict(lb=g["lb"][b], ub=g["ub"][b], failed=bool(g["failed"][b])), o, b)
+
+
+def test_infinite_and_extreme_bounds(eng, orc):
+    NI, PI = abi.NEG_INF, abi.POS_INF
+    big = 2 ** 31 - 2
+    lb = [0, 1, 2, NI, NI, 5, big, -big, NI, 0]
+    ub = [0, 1, 2, PI, 10, PI, big, -big, PI, 1]
+    props = [(abi.OP_ADD, 3, 4, 5), (abi.OP_ADD, 8, 6, 6), (abi.OP_ADD, 8, 7, 7), (abi.OP_LEQ, 1, 3, 4),
+             (abi.OP_LEQ, 9, 5, 4), (abi.OP_MUL, 8, 6, 2), (abi.OP_MAX, 3, 4, 5), (abi.OP_EQ, 0, 4, 5)]
+    for k in range(1, len(props) + 1):
+        pb = abi.Problem(lb, ub, np.array(props[:k], np.int32))
+        o = orc.fixpoint(pb)
+        for kind in KINDS:
+            with eng.Solver(pb, mem_kind=kind) as s:
+                g = s.propagate()
+            assert_same_store(g, o, (k, kind))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_every_dive_subproblem_bit_exact(eng, orc, kind):
+    for seed, depth in [(11, 4), (12, 6), (13, 5)]:
+        strat = [(abi.VAR_INPUT_ORDER, abi.VAL_SPLIT, list(range(3, 40))), (abi.VAR_FIRST_FAIL, abi.VAL_MIN, [])]
+        pb = tnf_gen.planted(120, 200, seed, strategies=strat, objective=True)
+        with eng.Solver(pb, mem_kind=kind) as s:
+            g = s.dive_batch(0, 1 << depth, depth)
+        for idx in range(1 << depth):
+            o = orc.dive(pb, idx, depth)
+            assert g["remaining_depth"][idx] == o["remaining_depth"], (seed, idx)
+            assert g["leaf_kind"][idx] == o["leaf_kind"], (seed, idx)
+            if o["leaf_kind"] != 1:
+                assert np.array_equal(g["lb"][idx], o["lb"]) and np.array_equal(g["ub"][idx], o["ub"]), (seed, idx)
+
+
+@pytest.mark.parametrize("var_order", range(5))
+@pytest.mark.parametrize("val_order", range(4))
+def test_dive_all_orders(eng, orc, var_order, val_order):
+    strat = [(var_order, val_order, list(range(3, 30))), (abi.VAR_FIRST_FAIL, abi.VAL_MIN, [])]
+    pb = tnf_gen.planted(60, 90, 21, strategies=strat)
+    depth = 5
+    with eng.Solver(pb) as s:
+        g = s.dive_batch(0, 1 << depth, depth)
+    for idx in range(1 << depth):
+        o = orc.dive(pb, idx, depth)
+        assert g["remaining_depth"][idx] == o["remaining_depth"] and g["leaf_kind"][idx] == o["leaf_kind"]
+        if o["leaf_kind"] != 1:
+            assert np.array_equal(g["lb"][idx], o["lb"]) and np.array_equal(g["ub"][idx], o["ub"])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_solve_status_and_optimum(eng, orc, kind):
+    for seed in range(25):
+        pb = tnf_gen.random_net(16, 18, 3000 + seed, lo=-4, hi=4)
+        o = orc.solve(pb, depth=0)
+        with eng.Solver(pb, mem_kind=kind, subproblems_power=4) as s:
+            g = s.solve()
+        assert g["exhaustive"] and o["exhaustive"]
+        assert g["has_solution"] == o["has_solution"], seed
+        assert g["objective"] == o["objective"], seed
+        if g["has_solution"]:
+            from tests.test_oracle_ops import REL
+            for p in pb.props:
+                assert REL[int(p["op"])](int(g["lb"][p["x"]]), int(g["lb"][p["y"]]), int(g["lb"][p["z"]]))
+
+
+def test_single_block_node_counts_match_oracle(eng, orc):
+    """With one block the subproblems are visited in index order exactly like the oracle, so the
+    whole trace (nodes, failures, solutions, skipped/solved subproblems, depth) is comparable."""
+    for seed in range(10):
+        pb = tnf_gen.random_net(18, 20, 4000 + seed, lo=-4, hi=4)
+        for depth in (0, 3):
+            o = orc.solve(pb, depth=depth)
+            with eng.Solver(pb, or_blocks=1, subproblems_power=depth, fixpoint=abi.FP_AC1) as s:
+                g = s.solve()
+            for key in ("nodes", "fails", "solutions", "eps_solved_subproblems", "eps_skipped_subproblems", "depth_max"):
+                assert g["stats"][key] == o["stats"][key], (seed, depth, key, g["stats"][key], o["stats"][key])
+            assert g["objective"] == o["objective"]
+
+
+def test_satisfaction(eng, orc):
+    pb = tnf_gen.planted(60, 80, 5, objective=False)
+    with eng.Solver(pb, subproblems_power=3) as s:
+        g = s.solve()
+    assert g["has_solution"] and not g["exhaustive"]
+    from tests.test_oracle_ops import REL
+    for p in pb.props:
+        assert REL[int(p["op"])](int(g["lb"][p["x"]]), int(g["lb"][p["y"]]), int(g["lb"][p["z"]]))
+
+
+def test_cutnodes_and_stop(eng):
+    pb = tnf_gen.planted(300, 500, 9, objective=True, slack=200)
+    with eng.Solver(pb, cutnodes=50) as s:
+        g = s.solve()
+    assert not g["exhaustive"]
+    assert g["stats"]["nodes"] <= 50 * g["stats"]["num_blocks"] + g["stats"]["num_blocks"]
+    with eng.Solver(pb, timeout_ms=200) as s:
+        g = s.solve()
+    assert g["stats"]["timers_ns"][abi.TIMER_OVERALL] < 5e9

@@ -1,0 +1,1272 @@
+// engine.cu — B200-native dive-and-solve engine behind the C ABI of include/turbo_b200.h.
+//
+// Replaces the device hot path of the reference's barebones architecture
+// (include/barebones_dive_and_solve.hpp:620-1067) and its launch glue (:464-606,
+// include/memory_gpu.hpp).  Design (DESIGN.md has the full story):
+//   * one persistent CTA per search worker; the interval store lives in shared memory
+//     (STORE_SHARED / TCN_SHARED), striped over a thread-block cluster's distributed shared memory
+//     (STORE_CLUSTER, cluster.cu) or in L2-resident global memory (GLOBAL);
+//   * propagators are immutable, packed to 8 bytes (op:4 | x:20 | y:20 | z:20) when #vars <= 2^20
+//     and streamed coalesced (one 64-bit load per lane) from L2, or staged once into shared memory;
+//   * the fixpoint loop publishes narrowed bounds with shared-memory atomicMax/atomicMin, detects
+//     "changed / failed / not entailed" with a warp REDUX + one atomicOr per warp into a rotating
+//     three-slot flag word: one __syncthreads per sweep; entailment (`ask`) is fused into the
+//     final sweep instead of a separate pass;
+//   * snapshot / restore-from-root / best-store copies are TMA bulk copies (cp.async.bulk) between
+//     global and shared memory, completion tracked by an mbarrier;
+//   * branching, the decision stack with ropes, the EPS dive and the subproblem dispenser all run
+//     in the kernel: no host round trip per node.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/turbo_b200.h"
+#include "engine_internal.h"
+#include "tnf_device.cuh"
+
+// ================================================================================================
+// device helpers
+// ================================================================================================
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// ---- TMA bulk copies (SASS: UBLKCP) -------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* mbar, unsigned phase) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s_issue(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_issue(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// The bulk-copy unit takes sizes that are multiples of 16 B; one instruction moves at most this
+// many bytes so that the mbarrier transaction count (20 bits) never overflows.
+#define BULK_CHUNK (128u * 1024u)
+
+// ================================================================================================
+// block context
+// ================================================================================================
+
+struct Ctl {                       // per-CTA control block in static shared memory
+  unsigned long long mbar;
+  unsigned long long sel_key;      // arg-min key of the variable selection
+  unsigned long long subproblem_k; // local subproblem counter value being solved
+  int flags[3];                    // rotating fixpoint flag words
+  int sel_first;
+  int stop, leaf, failed;
+  int remaining_depth, depth, cur_strategy, next_unassigned, snap_strategy, snap_next_unassigned;
+  int best_bound;
+  int pushed;
+  long long t_mark;
+};
+
+template <int MEM, bool AOS>
+struct StoreRef {
+  int* p;      // shared (MEM != GLOBAL) or global
+  int vpad;
+  __device__ __forceinline__ void ld(int v, int& l, int& u) const {
+    if (AOS) {
+      int2 t = (MEM == TB_MEM_GLOBAL) ? __ldcg((const int2*)(p + 2 * v)) : *(const int2*)(p + 2 * v);
+      l = t.x; u = t.y;
+    } else {
+      l = (MEM == TB_MEM_GLOBAL) ? __ldcg(p + v) : p[v];
+      u = (MEM == TB_MEM_GLOBAL) ? __ldcg(p + vpad + v) : p[vpad + v];
+    }
+  }
+  __device__ __forceinline__ int* lbp(int v) const { return AOS ? p + 2 * v : p + v; }
+  __device__ __forceinline__ int* ubp(int v) const { return AOS ? p + 2 * v + 1 : p + vpad + v; }
+  __device__ __forceinline__ void tell_lb(int v, int n) const { atomicMax(lbp(v), n); }
+  __device__ __forceinline__ void tell_ub(int v, int n) const { atomicMin(ubp(v), n); }
+  // VStore::embed (barebones :707,761-764,805,846,853): in-place meet, returns "changed"
+  __device__ __forceinline__ bool embed(int v, int l, int u) const {
+    int ol = atomicMax(lbp(v), l), ou = atomicMin(ubp(v), u);
+    return l > ol || u < ou;
+  }
+};
+
+template <bool PACKED>
+__device__ __forceinline__ void load_prop(const void* props, int i, int& op, int& x, int& y, int& z, bool in_smem) {
+  if (PACKED) {
+    unsigned long long w = in_smem ? ((const unsigned long long*)props)[i] : __ldg((const unsigned long long*)props + i);
+    op = (int)(w >> 60); x = (int)((w >> 40) & 0xFFFFFu); y = (int)((w >> 20) & 0xFFFFFu); z = (int)(w & 0xFFFFFu);
+  } else {
+    int4 w = in_smem ? ((const int4*)props)[i] : __ldg((const int4*)props + i);
+    op = w.x; x = w.y; y = w.z; z = w.w;
+  }
+}
+
+// One evaluation of one propagator: 6 loads, candidates in registers, publish what narrows.
+template <class Store>
+__device__ __forceinline__ int deduce(const Store& s, int op, int x, int y, int z, unsigned& narrowed) {
+  int xl, xu, yl, yu, zl, zu;
+  s.ld(x, xl, xu); s.ld(y, yl, yu); s.ld(z, zl, zu);
+  if ((xl > xu) | (yl > yu) | (zl > zu)) return F_FAILED | F_NOT_ENTAILED;
+  tbd::Cand c;
+  int bits = tbd::eval(op, xl, xu, yl, yu, zl, zu, c);
+  if (c.xl > xl) { s.tell_lb(x, c.xl); bits |= F_CHANGED | (c.xl > xu ? F_FAILED : 0); ++narrowed; }
+  if (c.xu < xu) { s.tell_ub(x, c.xu); bits |= F_CHANGED | (c.xu < xl ? F_FAILED : 0); ++narrowed; }
+  if (c.yl > yl) { s.tell_lb(y, c.yl); bits |= F_CHANGED | (c.yl > yu ? F_FAILED : 0); ++narrowed; }
+  if (c.yu < yu) { s.tell_ub(y, c.yu); bits |= F_CHANGED | (c.yu < yl ? F_FAILED : 0); ++narrowed; }
+  if (c.zl > zl) { s.tell_lb(z, c.zl); bits |= F_CHANGED | (c.zl > zu ? F_FAILED : 0); ++narrowed; }
+  if (c.zu < zu) { s.tell_ub(z, c.zu); bits |= F_CHANGED | (c.zu < zl ? F_FAILED : 0); ++narrowed; }
+  return bits;
+}
+
+template <int MEM, bool AOS, bool PACKED>
+struct Ctx {
+  const DevParams& P;
+  Ctl& c;
+  StoreRef<MEM, AOS> store;
+  const void* props;       // global or shared
+  bool props_in_smem;
+  unsigned mbar_phase;
+  unsigned narrowed;       // per-thread count of published bounds
+  unsigned long long deductions_wac1;  // per-warp (lane-uniform) inner iterations
+  int* g_root;             // this block's snapshot (global, same layout as the store)
+  int* g_best;
+  Decision* dec;
+  BlockStats* st;
+
+  __device__ Ctx(const DevParams& P_, Ctl& c_) : P(P_), c(c_) {}
+
+  // ---- copies between the block store and a global image of it ---------------------------------
+  __device__ void load_store(const int* gsrc) {
+    const unsigned bytes = (unsigned)P.vpad * 8u;
+    if (MEM == TB_MEM_GLOBAL) {
+      __syncthreads();
+      const int4* s4 = (const int4*)gsrc; int4* d4 = (int4*)store.p;
+      for (unsigned i = threadIdx.x; i < bytes / 16; i += blockDim.x) d4[i] = __ldcg(s4 + i);
+      __syncthreads();
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&c.mbar, bytes);
+        for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
+          bulk_g2s_issue((char*)store.p + off, (const char*)gsrc + off, min(BULK_CHUNK, bytes - off), &c.mbar);
+      }
+      while (!mbar_try_wait(&c.mbar, mbar_phase)) {}
+      mbar_phase ^= 1;
+    }
+  }
+  __device__ void save_store(int* gdst) {
+    const unsigned bytes = (unsigned)P.vpad * 8u;
+    __syncthreads();
+    if (MEM == TB_MEM_GLOBAL) {
+      const int4* s4 = (const int4*)store.p; int4* d4 = (int4*)gdst;
+      for (unsigned i = threadIdx.x; i < bytes / 16; i += blockDim.x) d4[i] = __ldcg(s4 + i);
+    } else if (threadIdx.x == 0) {
+      fence_proxy_async();
+      for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
+        bulk_s2g_issue((char*)gdst + off, (const char*)store.p + off, min(BULK_CHUNK, bytes - off));
+      bulk_commit_wait_all();
+    }
+    __syncthreads();
+  }
+
+  // ---- fixpoint (BlockAsynchronousFixpointGPU::fixpoint + warp_fixpoint, barebones :925-965) ---
+  // Returns the OR of the flag bits of the last sweep; `iters` = number of block sweeps.
+  __device__ int fixpoint(int& iters) {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
+    const int n = P.nprops_pad;
+    int it = 0, f;
+    for (;; ++it) {
+      int bits = 0;
+      if (wac1) {
+        for (int base = tid - lane; base < n; base += T) {
+          int op, x, y, z;
+          load_prop<PACKED>(props, base + lane, op, x, y, z, props_in_smem);
+          int b, wsticky = 0;          // wsticky is warp-uniform: every exit below is taken by the whole warp
+          bool again;
+          do {
+            b = deduce(store, op, x, y, z, narrowed);
+            const int wb = __reduce_or_sync(0xffffffffu, b);
+            wsticky |= wb;
+            ++deductions_wac1;
+            again = (wb & F_CHANGED) && !(wb & F_FAILED);
+            __syncwarp();
+          } while (again);
+          bits |= (wsticky & (F_CHANGED | F_FAILED)) | (b & F_NOT_ENTAILED);
+          if (wsticky & F_FAILED) break;
+        }
+      } else {
+        for (int i = tid; i < n; i += T) {
+          int op, x, y, z;
+          load_prop<PACKED>(props, i, op, x, y, z, props_in_smem);
+          bits |= deduce(store, op, x, y, z, narrowed);
+        }
+      }
+      bits = __reduce_or_sync(0xffffffffu, bits);
+      const int slot = it % 3;
+      if (lane == 0 && bits) atomicOr(&c.flags[slot], bits);
+      if (tid == 0) c.flags[(it + 1) % 3] = 0;
+      __syncthreads();
+      f = c.flags[slot];
+      if (!(f & F_CHANGED) || (f & F_FAILED)) break;
+    }
+    iters = it + 1;
+    // leave slot 0 clean for the next call (nobody reads flags until the next fixpoint's barrier)
+    __syncthreads();
+    if (tid < 3) c.flags[tid] = 0;
+    __syncthreads();
+    return f;
+  }
+
+  // ---- propagate() (barebones :903-1031) -----------------------------------------------------------
+  // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
+  // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
+  __device__ void propagate() {
+    const int tid = threadIdx.x;
+    unsigned long long t0 = 0;
+    if (tid == 0) t0 = globaltimer_ns();
+    int iters = 0, f;
+    bool obj_empty = false;
+    if (P.obj_var >= 0) { int l, u; store.ld(P.obj_var, l, u); obj_empty = l > u; }
+    if (obj_empty) f = F_FAILED;
+    else f = fixpoint(iters);
+    const bool failed = (f & F_FAILED) != 0;
+    const bool solution = !failed && !(f & F_NOT_ENTAILED);
+    unsigned long long t1 = 0;
+    if (tid == 0) t1 = globaltimer_ns();
+    bool improved = false;
+    if (solution) {
+      if (P.obj_var >= 0) {
+        int l, u; store.ld(P.obj_var, l, u);
+        improved = c.best_bound > l;           // uniform: same smem word read by everybody
+        __syncthreads();
+        if (improved && tid == 0) {
+          c.best_bound = l;
+          atomicMin(P.appx_best_bound, l);
+          for (int g = 0; g < P.npeers; ++g) atomicMin_system(P.peer_bounds[g], l);
+          st->t_best = (long long)(globaltimer_ns() - P.t_start);
+          st->best_bound = l;
+        }
+      } else {
+        improved = st->solutions == 0;          // satisfaction: first solution wins
+        __syncthreads();
+        if (tid == 0) st->t_best = (long long)(globaltimer_ns() - P.t_start);
+      }
+      if (improved) {
+        save_store(g_best);
+        if (tid == 0) { st->solutions++; st->has_best = 1; }
+      }
+    }
+    if (tid == 0) {
+      c.leaf = failed || solution;
+      c.failed = failed;
+      st->fixpoint_iterations += (unsigned long long)iters;
+      st->nodes++;
+      st->fails += failed ? 1 : 0;
+      if (c.depth > st->depth_max) st->depth_max = c.depth;
+      st->t_fixpoint += (long long)(t1 - t0);
+      if (solution && P.obj_var < 0) {       // satisfaction: stop everybody after the first solution
+        st->exhaustive = 0;
+        c.stop = 1;
+        *P.stop = 1;
+      }
+      if ((P.cutnodes && st->nodes >= P.cutnodes) || *P.stop) {
+        st->exhaustive = 0;
+        c.stop = 1;
+      }
+    }
+    if (!(P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold) && tid == 0)
+      st->deductions += (unsigned long long)iters * (unsigned long long)P.nprops;
+    __syncthreads();
+  }
+
+  // ---- branching (BlockData::split / push_decision, barebones :187-405) ----------------------------
+  __device__ __forceinline__ unsigned long long sel_key(int order, int l, int u, int i) const {
+    unsigned hi;
+    switch (order) {
+      case TB_VAR_INPUT_ORDER:     hi = 0u; break;
+      case TB_VAR_FIRST_FAIL:      hi = (unsigned)u - (unsigned)l; break;
+      case TB_VAR_ANTI_FIRST_FAIL: hi = ~((unsigned)u - (unsigned)l); break;
+      case TB_VAR_SMALLEST:        hi = (unsigned)l ^ 0x80000000u; break;
+      default:                     hi = ~((unsigned)u ^ 0x80000000u); break;   // LARGEST
+    }
+    return ((unsigned long long)hi << 32) | (unsigned)i;
+  }
+
+  // thread 0 only
+  __device__ void push_decision(int val_order, int var) {
+    if (c.depth >= P.max_depth) { st->error = TB_ERR_DEPTH; st->exhaustive = 0; c.stop = 1; *P.stop = 1; c.pushed = 0; return; }
+    int l, u; store.ld(var, l, u);
+    Decision d;
+    d.var = var; d.cur = -1;
+    int mid = (int)((long long)l + ((long long)u - (long long)l) / 2);
+    switch (val_order) {
+      case TB_VAL_MIN:   d.clb0 = l; d.cub0 = l; d.clb1 = l + 1; d.cub1 = u; break;
+      case TB_VAL_MAX:   d.clb0 = u; d.cub0 = u; d.clb1 = l; d.cub1 = u - 1; break;
+      case TB_VAL_SPLIT: d.clb0 = l; d.cub0 = mid; d.clb1 = mid + 1; d.cub1 = u; break;
+      default:           d.clb0 = mid + 1; d.cub0 = u; d.clb1 = l; d.cub1 = mid; break;
+    }
+    d.rope0 = c.depth + 1;
+    if (c.depth > 0) { const Decision& p = dec[c.depth - 1]; d.rope1 = p.cur == 0 ? p.rope0 : p.rope1; }
+    else d.rope1 = -1;
+    dec[c.depth] = d;
+    c.depth++;
+    c.pushed = 1;
+  }
+
+  // Returns (uniformly) whether a decision was pushed at dec[depth-1].
+  __device__ bool split() {
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    for (;;) {
+      const int s = c.cur_strategy;       // uniform (barrier before every read)
+      if (s >= P.nstrategies) return false;
+      const DevStrategy strat = P.strategies[s];
+      const bool in_store = strat.n == 0;
+      const int n = in_store ? P.nvars : strat.n;
+      unsigned long long key = ~0ull;
+      int first = INT32_MAX;
+      for (int i = c.next_unassigned + tid; i < n; i += T) {
+        int v = in_store ? i : __ldg(strat.vars + i);
+        int l, u; store.ld(v, l, u);
+        if (l != u && l != TBD_NINF && u != TBD_PINF) {
+          if (first == INT32_MAX) first = i;
+          unsigned long long k = sel_key(strat.var_order, l, u, i);
+          if (k < key) key = k;
+          if (strat.var_order == TB_VAR_INPUT_ORDER) break;
+        }
+      }
+      first = __reduce_min_sync(0xffffffffu, first);
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        if (other < key) key = other;
+      }
+      if (lane == 0 && key != ~0ull) { atomicMin(&c.sel_key, key); atomicMin(&c.sel_first, first); }
+      __syncthreads();
+      const unsigned long long best = c.sel_key;
+      __syncthreads();
+      if (tid == 0) {
+        if (best != ~0ull) {
+          c.next_unassigned = c.sel_first;
+          int i = (int)(unsigned)(best & 0xffffffffu);
+          push_decision(strat.val_order, in_store ? i : strat.vars[i]);
+        } else {
+          c.cur_strategy = s + 1;
+          c.next_unassigned = 0;
+        }
+        c.sel_key = ~0ull; c.sel_first = INT32_MAX;
+      }
+      __syncthreads();
+      if (best != ~0ull) return c.pushed != 0;
+    }
+  }
+
+  // ---- EPS dive (barebones :663-741) ------------------------------------------------------------------
+  // Dives from the problem root following the bits of `idx`. Returns remaining depth (uniform).
+  __device__ int dive(unsigned long long idx, int depth_power) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+      c.cur_strategy = 0; c.next_unassigned = 0; c.depth = 0;
+      c.remaining_depth = depth_power; c.leaf = 0; c.failed = 0;
+      c.t_mark = (long long)globaltimer_ns();
+    }
+    load_store(P.root_store);
+    __syncthreads();
+    while (c.remaining_depth > 0 && !c.leaf && !c.stop) {
+      __syncthreads();
+      propagate();
+      if (!c.leaf) {
+        bool pushed = split();
+        if (tid == 0) {
+          if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
+          else {
+            --c.remaining_depth;
+            --c.depth;                        // decisions are not recorded while diving
+            const Decision& d = dec[0];
+            int bit = (int)((idx >> c.remaining_depth) & 1ull);
+            store.embed(d.var, bit ? d.clb1 : d.clb0, bit ? d.cub1 : d.cub0);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) st->t_dive += (long long)globaltimer_ns() - c.t_mark;
+    __syncthreads();
+    return c.remaining_depth;
+  }
+
+  // ---- solve one subproblem (barebones :742-871) -----------------------------------------------------
+  __device__ void solve_subproblem() {
+    const int T = blockDim.x, tid = threadIdx.x;
+    if (tid == 0 && P.has_eps_strategy) { c.cur_strategy = max(1, c.cur_strategy); c.next_unassigned = 0; }
+    __syncthreads();
+    while (!c.stop) {
+      // I. inject the incumbent bound (thread 0), detect an unconstrained objective
+      if (tid == 0 && P.obj_var >= 0) {
+        int appx = *(volatile int*)P.appx_best_bound;
+        if (appx != TBD_PINF) {
+          store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
+          store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
+        }
+        if (appx == TBD_NINF) { c.stop = 1; *P.stop = 1; }
+      }
+      __syncthreads();
+      if (c.stop) break;
+      // II. propagate
+      propagate();
+      // III. branch
+      if (!c.leaf) {
+        if (c.depth == 0) {
+          save_store(g_root);
+          if (tid == 0) { c.snap_strategy = c.cur_strategy; c.snap_next_unassigned = c.next_unassigned; }
+          __syncthreads();
+        }
+        bool pushed = split();
+        if (tid == 0) {
+          if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
+          else {
+            Decision& d = dec[c.depth - 1];
+            d.cur = 0;
+            store.embed(d.var, d.clb0, d.cub0);
+          }
+        }
+        __syncthreads();
+      }
+      // IV. backtrack: follow the rope, restore from the subproblem root, replay the decisions
+      if (c.leaf) {
+        if (c.depth == 0) break;
+        __syncthreads();
+        if (tid == 0) { const Decision& d = dec[c.depth - 1]; c.depth = d.cur == 0 ? d.rope0 : d.rope1; }
+        __syncthreads();
+        const int depth = c.depth;
+        if (depth == -1) break;
+        load_store(g_root);
+        for (int i = tid; i < depth - 1; i += T) {
+          const Decision d = dec[i];
+          store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+        }
+        if (tid == 0) {
+          Decision& d = dec[depth - 1];
+          d.cur += 1;
+          store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+          c.cur_strategy = c.snap_strategy; c.next_unassigned = c.snap_next_unassigned;
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+};
+
+// ---- context construction shared by the three kernels -----------------------------------------------
+template <int MEM, bool AOS, bool PACKED>
+__device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, unsigned char* dyn, int slot) {
+  const DevParams& P = k.P;
+  Ctl& c = k.c;
+  const size_t store_bytes = (size_t)P.vpad * 8;
+  k.store.vpad = P.vpad;
+  k.store.p = (MEM == TB_MEM_GLOBAL) ? P.block_store + (size_t)slot * 2 * P.vpad : (int*)dyn;
+  k.props = P.props;
+  k.props_in_smem = false;
+  k.mbar_phase = 0;
+  k.narrowed = 0;
+  k.deductions_wac1 = 0;
+  k.g_root = P.block_root + (size_t)slot * 2 * P.vpad;
+  k.g_best = P.block_best + (size_t)slot * 2 * P.vpad;
+  k.dec = P.decisions + (size_t)slot * P.max_depth;
+  k.st = P.stats + slot;
+  if (threadIdx.x == 0) {
+    mbar_init(&c.mbar, 1);
+    c.flags[0] = c.flags[1] = c.flags[2] = 0;
+    c.sel_key = ~0ull; c.sel_first = INT32_MAX;
+    c.stop = 0; c.leaf = 0; c.failed = 0; c.depth = 0; c.pushed = 0;
+    c.cur_strategy = 0; c.next_unassigned = 0; c.snap_strategy = 0; c.snap_next_unassigned = 0;
+    c.best_bound = TBD_PINF; c.remaining_depth = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (MEM == TB_MEM_TCN_SHARED) {
+    // stage the propagator table once: TMA bulk copy global -> shared
+    unsigned char* sprops = dyn + store_bytes;
+    const unsigned bytes = (unsigned)((size_t)P.nprops_pad * (PACKED ? 8 : 16));
+    if (threadIdx.x == 0 && bytes) {
+      fence_proxy_async();
+      mbar_expect_tx(&c.mbar, bytes);
+      for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
+        bulk_g2s_issue(sprops + off, (const char*)P.props + off, min(BULK_CHUNK, bytes - off), &c.mbar);
+    }
+    if (bytes) { while (!mbar_try_wait(&c.mbar, k.mbar_phase)) {} k.mbar_phase ^= 1; }
+    k.props = sprops;
+    k.props_in_smem = true;
+  }
+}
+
+template <int MEM, bool AOS, bool PACKED>
+__device__ __forceinline__ void ctx_finish(Ctx<MEM, AOS, PACKED>& k) {
+  // fold the per-thread / per-warp counters into the block statistics
+  unsigned n = k.narrowed;
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&k.st->narrowed, (unsigned long long)n);
+    if (k.deductions_wac1) atomicAdd(&k.st->deductions, k.deductions_wac1 * 32ull);
+  }
+}
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+
+// The persistent dive-and-solve kernel (gpu_barebones_solve, barebones :620-901).
+template <int MEM, bool AOS, bool PACKED>
+__global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ DevParams P) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ Ctl c;
+  Ctx<MEM, AOS, PACKED> k(P, c);
+  ctx_init(k, dyn, blockIdx.x);
+  const int tid = threadIdx.x;
+  BlockStats* st = k.st;
+  if (tid == 0) c.subproblem_k = blockIdx.x;
+  __syncthreads();
+  const unsigned long long nsub = P.num_subproblems;
+  const unsigned long long world = (unsigned long long)P.world, rank = (unsigned long long)P.rank;
+  for (;;) {
+    const unsigned long long idx = c.subproblem_k * world + rank;   // this GPU's shard: idx ≡ rank (mod world)
+    if (idx >= nsub || c.stop) break;
+    __syncthreads();
+    const int remaining = k.dive(idx, P.subproblems_power);
+    if (c.leaf && !c.stop) {
+      // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
+      if (tid == 0) {
+        unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
+        unsigned long long next_k = next <= rank ? 0ull : (next - rank + world - 1ull) / world;
+        atomicMax(P.next_subproblem, next_k);
+        if ((idx & ((1ull << remaining) - 1ull)) == 0ull) st->eps_skipped += next - idx;
+      }
+    } else if (!c.stop) {
+      k.solve_subproblem();
+      if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->eps_solved += 1;
+    }
+    __syncthreads();
+    if (tid == 0 && !c.stop) c.subproblem_k = atomicAdd(P.next_subproblem, 1ull);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (!(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->blocks_done = 1;
+    st->t_idle = (long long)(globaltimer_ns() - P.t_start);
+  }
+  ctx_finish(k);
+}
+
+// One fixpoint per block on caller-provided stores (tb_propagate / tb_propagate_batch).
+template <int MEM, bool AOS, bool PACKED>
+__global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__ DevParams P, int nstores,
+                                                         const int* in_lb, const int* in_ub,
+                                                         int* out_lb, int* out_ub, int* out_failed, int repeat) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ Ctl c;
+  Ctx<MEM, AOS, PACKED> k(P, c);
+  ctx_init(k, dyn, blockIdx.x);
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int s = blockIdx.x; s < nstores; s += gridDim.x) {
+    int f = 0, iters = 0;
+    for (int r = 0; r < repeat; ++r) {
+      __syncthreads();
+      for (int v = tid; v < P.vpad; v += T) {
+        int l = 0, u = 0;
+        if (v < P.nvars) { l = in_lb[(size_t)s * P.nvars + v]; u = in_ub[(size_t)s * P.nvars + v]; }
+        *k.store.lbp(v) = l; *k.store.ubp(v) = u;
+      }
+      __syncthreads();
+      f = k.fixpoint(iters);
+      if (tid == 0) {
+        k.st->fixpoint_iterations += (unsigned long long)iters;
+        k.st->nodes++;
+        if (!(P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold))
+          k.st->deductions += (unsigned long long)iters * (unsigned long long)P.nprops;
+      }
+    }
+    __syncthreads();
+    for (int v = tid; v < P.nvars; v += T) {
+      int l, u; k.store.ld(v, l, u);
+      out_lb[(size_t)s * P.nvars + v] = l; out_ub[(size_t)s * P.nvars + v] = u;
+    }
+    if (tid == 0) out_failed[s] = (f & F_FAILED) ? 1 : 0;
+  }
+  ctx_finish(k);
+}
+
+// EPS dive only (tb_dive / tb_dive_batch).
+template <int MEM, bool AOS, bool PACKED>
+__global__ void __launch_bounds__(1024) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
+                                                    int depth, int* out_lb, int* out_ub, int* out_remaining, int* out_kind) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ Ctl c;
+  Ctx<MEM, AOS, PACKED> k(P, c);
+  ctx_init(k, dyn, blockIdx.x);
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int s = blockIdx.x; s < count; s += gridDim.x) {
+    __syncthreads();
+    int remaining = k.dive(first + (unsigned long long)s, depth);
+    __syncthreads();
+    for (int v = tid; v < P.nvars; v += T) {
+      int l, u; k.store.ld(v, l, u);
+      out_lb[(size_t)s * P.nvars + v] = l; out_ub[(size_t)s * P.nvars + v] = u;
+    }
+    if (tid == 0) { out_remaining[s] = remaining; out_kind[s] = c.leaf ? (c.failed ? 1 : 2) : 0; }
+  }
+  ctx_finish(k);
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+extern "C" const char* tb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* tb_version(void) { return "turbo-b200 0.1.0 (sm_100a)"; }
+void tb_set_error_internal(const char* s) { set_error(s); }
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+      return TB_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+extern "C" int32_t tb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+struct tb_solver {
+  DevParams P;
+  tb_options opt;
+  int device = 0;
+  int nvars = 0, nprops = 0;
+  int mem_kind = TB_MEM_GLOBAL, threads = 256, num_blocks = 1, blocks_per_sm = 1, cluster = 1;
+  bool aos = false, packed = true;
+  size_t shared_bytes = 0, store_bytes = 0, prop_bytes = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  std::vector<void*> allocs;
+  std::vector<int*> peer_cells;       // device pointers to other GPUs' incumbent cells
+  std::vector<void*> ipc_opened;
+  int** d_peer_array = nullptr;
+  int* d_bound = nullptr;
+  int* d_stop = nullptr;
+  unsigned long long* d_next = nullptr;
+  int scratch_blocks = 0;             // number of per-block scratch slots allocated
+  // batch buffers (grown on demand)
+  int *d_in_lb = nullptr, *d_in_ub = nullptr, *d_out_lb = nullptr, *d_out_ub = nullptr, *d_out_i0 = nullptr, *d_out_i1 = nullptr;
+  size_t batch_cap = 0;
+  int32_t* h_pinned_one = nullptr;
+};
+
+template <class T>
+static tb_status dev_alloc(tb_solver* s, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? TB_ERR_NOMEM : TB_ERR_CUDA; }
+  s->allocs.push_back(q);
+  *p = (T*)q;
+  return TB_OK;
+}
+
+// kernel dispatch over (placement, store layout, propagator format)
+template <class F>
+static tb_status dispatch(const tb_solver* s, F&& f) {
+#define TB_CASE(M)                                                                                   \
+  case M:                                                                                            \
+    if (s->aos) { if (s->packed) return f(std::integral_constant<int, M>{}, std::true_type{}, std::true_type{});   \
+                  else return f(std::integral_constant<int, M>{}, std::true_type{}, std::false_type{}); }           \
+    else        { if (s->packed) return f(std::integral_constant<int, M>{}, std::false_type{}, std::true_type{});  \
+                  else return f(std::integral_constant<int, M>{}, std::false_type{}, std::false_type{}); }
+  switch (s->mem_kind) {
+    TB_CASE(TB_MEM_GLOBAL)
+    TB_CASE(TB_MEM_STORE_SHARED)
+    TB_CASE(TB_MEM_TCN_SHARED)
+    default: break;
+  }
+#undef TB_CASE
+  set_error("unsupported memory kind");
+  return TB_ERR_UNSUPPORTED;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// Placement policy: MemoryConfig (memory_gpu.hpp:43-84) + configure_gpu_barebones (barebones :527-606),
+// solved together with occupancy (the reference queries occupancy with 0 dynamic smem).
+static tb_status configure(tb_solver* s) {
+  cudaDeviceProp dp;
+  CU(cudaGetDeviceProperties(&dp, s->device));
+  s->num_sms = dp.multiProcessorCount;
+  const size_t max_block_smem = dp.sharedMemPerBlockOptin;               // 227 KB on sm_100
+  const size_t sm_smem = dp.sharedMemPerMultiprocessor;                  // 228 KB
+  const size_t reserved = dp.reservedSharedMemPerBlock + sizeof(Ctl) + 64;
+  const size_t store_b = s->store_bytes, prop_b = s->prop_bytes;
+  auto blocks_for = [&](size_t dyn) -> int {
+    if (dyn + sizeof(Ctl) + 64 > max_block_smem) return 0;
+    return (int)std::min<size_t>(32, sm_smem / (dyn + reserved));
+  };
+  int kind = s->opt.mem_kind;
+  const int b_tcn = blocks_for(store_b + prop_b), b_store = blocks_for(store_b);
+  if (kind == TB_MEM_AUTO) {
+    // Prefer the propagator table in shared memory unless that costs most of the resident blocks.
+    if (b_tcn >= 1 && (b_tcn >= 4 || b_tcn * 2 >= std::min(b_store, 8))) kind = TB_MEM_TCN_SHARED;
+    else if (b_store >= 1) kind = TB_MEM_STORE_SHARED;
+    else kind = TB_MEM_GLOBAL;    // STORE_CLUSTER is chosen by the cluster engine (cluster.cu) before we get here
+  }
+  if (kind == TB_MEM_TCN_SHARED && b_tcn < 1) { set_error("TCN_SHARED does not fit in shared memory"); return TB_ERR_INVALID; }
+  if (kind == TB_MEM_STORE_SHARED && b_store < 1) { set_error("STORE_SHARED does not fit in shared memory"); return TB_ERR_INVALID; }
+  s->mem_kind = kind;
+  s->shared_bytes = kind == TB_MEM_TCN_SHARED ? store_b + prop_b : (kind == TB_MEM_STORE_SHARED ? store_b : 0);
+  int bps = kind == TB_MEM_TCN_SHARED ? b_tcn : (kind == TB_MEM_STORE_SHARED ? b_store : 8);
+  // Threads: keep ~1024 resident threads per SM at <= 64 registers (the reference compiles 256/block).
+  int threads = s->opt.threads_per_block;
+  if (threads <= 0) {
+    bps = std::min(bps, 8);
+    threads = bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024);
+    // do not use more threads than there is work per sweep
+    while (threads > 128 && threads / 2 >= s->P.nprops_pad) threads /= 2;
+  }
+  threads = std::max(32, std::min(1024, (threads + 31) / 32 * 32));
+  bps = std::max(1, std::min(bps, 2048 / threads));
+  s->threads = threads;
+  s->blocks_per_sm = bps;
+  int blocks = bps * s->num_sms;
+  if (s->opt.or_blocks > 0) blocks = std::min(blocks, s->opt.or_blocks);
+  s->num_blocks = std::max(1, blocks);
+  s->blocks_per_sm = (s->num_blocks + s->num_sms - 1) / s->num_sms;
+  return TB_OK;
+}
+
+static tb_status set_smem_attr(tb_solver* s) {
+  return dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
+    constexpr int m = decltype(M)::value; constexpr bool a = decltype(A)::value; constexpr bool k = decltype(K)::value;
+    if (s->shared_bytes) {
+      CU(cudaFuncSetAttribute(solve_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(propagate_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(dive_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+    }
+    return TB_OK;
+  });
+}
+
+static tb_status ensure_scratch(tb_solver* s, int slots) {
+  if (slots <= s->scratch_blocks) return TB_OK;
+  DevParams& P = s->P;
+  tb_status rc;
+  const size_t img = (size_t)2 * P.vpad;
+  if ((rc = dev_alloc(s, &P.block_root, img * slots))) return rc;
+  if ((rc = dev_alloc(s, &P.block_best, img * slots))) return rc;
+  if (s->mem_kind == TB_MEM_GLOBAL) { if ((rc = dev_alloc(s, &P.block_store, img * slots))) return rc; }
+  if ((rc = dev_alloc(s, &P.decisions, (size_t)P.max_depth * slots))) return rc;
+  if ((rc = dev_alloc(s, &P.stats, (size_t)slots))) return rc;
+  s->scratch_blocks = slots;
+  return TB_OK;
+}
+
+extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_options* opt_in) {
+  if (!out || !pb) { set_error("null argument"); return TB_ERR_INVALID; }
+  *out = nullptr;
+  if (pb->nvars < 0 || pb->nprops < 0 || (pb->nvars && (!pb->lb || !pb->ub)) || (pb->nprops && !pb->props)) {
+    set_error("malformed tb_problem"); return TB_ERR_INVALID;
+  }
+  for (int i = 0; i < pb->nprops; ++i) {
+    const tb_prop& p = pb->props[i];
+    if (p.op < 0 || p.op >= TB_NUM_OPS || p.x < 0 || p.y < 0 || p.z < 0 || p.x >= pb->nvars || p.y >= pb->nvars || p.z >= pb->nvars) {
+      set_error("propagator " + std::to_string(i) + " has an invalid operator or variable index"); return TB_ERR_INVALID;
+    }
+  }
+  if (pb->obj_var >= pb->nvars) { set_error("obj_var out of range"); return TB_ERR_INVALID; }
+  for (int i = 0; i < pb->nstrategies; ++i) {
+    const tb_strategy& st = pb->strategies[i];
+    if (st.n < 0 || (st.n && !st.vars)) { set_error("malformed strategy"); return TB_ERR_INVALID; }
+    for (int j = 0; j < st.n; ++j) if (st.vars[j] < 0 || st.vars[j] >= pb->nvars) { set_error("strategy variable out of range"); return TB_ERR_INVALID; }
+  }
+  if (tb_device_count() <= 0) { set_error("no CUDA device visible: the engine has no CPU fallback"); return TB_ERR_NO_DEVICE; }
+
+  tb_options opt;
+  memset(&opt, 0, sizeof(opt));
+  if (opt_in) opt = *opt_in;
+  else { opt.fixpoint = TB_FP_WAC1; opt.subproblems_power = -1; opt.subproblems_factor = 300; opt.mem_kind = TB_MEM_AUTO; opt.gpu_world = 1; }
+  if (opt.gpu_world <= 0) { opt.gpu_world = 1; opt.gpu_rank = 0; }
+  if (opt.gpu_rank < 0 || opt.gpu_rank >= opt.gpu_world) { set_error("gpu_rank out of range"); return TB_ERR_INVALID; }
+  if (opt.subproblems_factor <= 0) opt.subproblems_factor = 300;
+  if (opt.mem_kind == TB_MEM_STORE_CLUSTER) { set_error("STORE_CLUSTER is served by the cluster engine"); return TB_ERR_UNSUPPORTED; }
+
+  tb_solver* s = new tb_solver();
+  s->opt = opt;
+  s->device = opt.device;
+  tb_status rc = TB_OK;
+  auto fail = [&](tb_status r) { tb_destroy(s); return r; };
+  if (cudaSetDevice(s->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(TB_ERR_CUDA); }
+  DevParams& P = s->P;
+  memset(&P, 0, sizeof(P));
+  s->nvars = pb->nvars; s->nprops = pb->nprops;
+  P.nvars = pb->nvars; P.nprops = pb->nprops;
+  P.vpad = std::max(4, (pb->nvars + 3) / 4 * 4);
+  P.nprops_pad = (pb->nprops + 31) / 32 * 32;
+  P.obj_var = pb->obj_var;
+  P.has_eps_strategy = pb->has_eps_strategy;
+  P.fixpoint_kind = opt.fixpoint == TB_FP_AC1 ? TB_FP_AC1 : TB_FP_WAC1;
+  P.wac1_threshold = opt.wac1_threshold;
+  P.cutnodes = opt.cutnodes;
+  P.rank = opt.gpu_rank; P.world = opt.gpu_world;
+  P.max_depth = opt.max_depth > 0 ? opt.max_depth : 10000;
+  s->packed = pb->nvars <= (1 << 20) && env_int("TB_PROP_FORMAT16", 0) == 0;
+  s->aos = env_int("TB_STORE_AOS", 0) != 0;
+  s->store_bytes = (size_t)P.vpad * 8;
+  s->prop_bytes = (size_t)P.nprops_pad * (s->packed ? 8 : 16);
+  if ((rc = configure(s)) != TB_OK) return fail(rc);
+  if ((rc = set_smem_attr(s)) != TB_OK) return fail(rc);
+
+  // ---- device images ---------------------------------------------------------------------------------
+  {
+    std::vector<int> img((size_t)2 * P.vpad, 0);
+    for (int v = 0; v < pb->nvars; ++v) {
+      if (s->aos) { img[2 * v] = pb->lb[v]; img[2 * v + 1] = pb->ub[v]; }
+      else { img[v] = pb->lb[v]; img[P.vpad + v] = pb->ub[v]; }
+    }
+    int* d = nullptr;
+    if ((rc = dev_alloc(s, &d, img.size()))) return fail(rc);
+    if (cudaMemcpy(d, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D root store"); return fail(TB_ERR_CUDA); }
+    P.root_store = d;
+  }
+  if (s->packed) {
+    std::vector<unsigned long long> w((size_t)P.nprops_pad, (unsigned long long)TB_OP_NOP << 60);
+    for (int i = 0; i < pb->nprops; ++i) {
+      const tb_prop& p = pb->props[i];
+      w[i] = ((unsigned long long)p.op << 60) | ((unsigned long long)p.x << 40) | ((unsigned long long)p.y << 20) | (unsigned long long)p.z;
+    }
+    unsigned long long* d = nullptr;
+    if ((rc = dev_alloc(s, &d, w.size()))) return fail(rc);
+    if (w.size() && cudaMemcpy(d, w.data(), w.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
+    P.props = d;
+  } else {
+    std::vector<tb_prop> w((size_t)P.nprops_pad, tb_prop{TB_OP_NOP, 0, 0, 0});
+    for (int i = 0; i < pb->nprops; ++i) w[i] = pb->props[i];
+    tb_prop* d = nullptr;
+    if ((rc = dev_alloc(s, &d, w.size()))) return fail(rc);
+    if (w.size() && cudaMemcpy(d, w.data(), w.size() * sizeof(tb_prop), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
+    P.props = d;
+  }
+  {
+    std::vector<DevStrategy> hs((size_t)std::max(1, pb->nstrategies));
+    for (int i = 0; i < pb->nstrategies; ++i) {
+      const tb_strategy& st = pb->strategies[i];
+      hs[i].var_order = st.var_order; hs[i].val_order = st.val_order; hs[i].n = st.n; hs[i].vars = nullptr;
+      if (st.n) {
+        int* dv = nullptr;
+        if ((rc = dev_alloc(s, &dv, (size_t)st.n))) return fail(rc);
+        if (cudaMemcpy(dv, st.vars, (size_t)st.n * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D strategy"); return fail(TB_ERR_CUDA); }
+        hs[i].vars = dv;
+      }
+    }
+    DevStrategy* d = nullptr;
+    if ((rc = dev_alloc(s, &d, hs.size()))) return fail(rc);
+    if (cudaMemcpy(d, hs.data(), hs.size() * sizeof(DevStrategy), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D strategies"); return fail(TB_ERR_CUDA); }
+    P.strategies = d; P.nstrategies = pb->nstrategies;
+  }
+  if ((rc = dev_alloc(s, &s->d_bound, 32))) return fail(rc);
+  if ((rc = dev_alloc(s, &s->d_stop, 32))) return fail(rc);
+  if ((rc = dev_alloc(s, &s->d_next, 4))) return fail(rc);
+  P.appx_best_bound = s->d_bound; P.stop = s->d_stop; P.next_subproblem = s->d_next;
+  P.peer_bounds = nullptr; P.npeers = 0;
+  if ((rc = ensure_scratch(s, s->num_blocks))) return fail(rc);
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&s->ev_start) != cudaSuccess || cudaEventCreate(&s->ev_stop) != cudaSuccess ||
+      cudaHostAlloc((void**)&s->h_pinned_one, 64, cudaHostAllocDefault) != cudaSuccess) {
+    set_error("stream/event creation failed"); return fail(TB_ERR_CUDA);
+  }
+  *s->h_pinned_one = 1;
+
+  // II. number of subproblems (barebones :548-555), generalised to the GPU count
+  int d = opt.subproblems_power;
+  if (d < 0) {
+    d = 0;
+    const unsigned long long want = (unsigned long long)opt.subproblems_factor * (unsigned long long)s->num_blocks * (unsigned long long)opt.gpu_world;
+    while ((1ull << d) < want && d < 62) ++d;
+  }
+  if (d > 62) d = 62;
+  P.subproblems_power = d;
+  P.num_subproblems = 1ull << d;
+  *out = s;
+  return TB_OK;
+}
+
+extern "C" void tb_destroy(tb_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (void* h : s->ipc_opened) cudaIpcCloseMemHandle(h);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->h_pinned_one) cudaFreeHost(s->h_pinned_one);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  if (s->ev_start) cudaEventDestroy(s->ev_start);
+  if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+  delete s;
+}
+
+static void fill_config(const tb_solver* s, tb_stats* st) {
+  st->num_blocks = s->num_blocks; st->threads_per_block = s->threads; st->mem_kind = s->mem_kind;
+  st->cluster_size = s->cluster; st->subproblems_power = s->P.subproblems_power; st->blocks_per_sm = s->blocks_per_sm;
+  st->shared_bytes = s->shared_bytes; st->store_bytes = s->store_bytes; st->prop_bytes = s->prop_bytes;
+  st->eps_num_subproblems = s->P.num_subproblems;
+}
+
+extern "C" tb_status tb_get_config(tb_solver* s, tb_stats* st) {
+  if (!s || !st) { set_error("null argument"); return TB_ERR_INVALID; }
+  memset(st, 0, sizeof(*st));
+  st->exhaustive = 1;
+  fill_config(s, st);
+  return TB_OK;
+}
+
+static tb_status reset_stats(tb_solver* s, int slots) {
+  std::vector<BlockStats> z((size_t)slots);
+  memset(z.data(), 0, z.size() * sizeof(BlockStats));
+  for (auto& b : z) { b.exhaustive = 1; b.best_bound = TBD_PINF; }
+  CU(cudaMemcpyAsync(s->P.stats, z.data(), z.size() * sizeof(BlockStats), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return TB_OK;
+}
+
+// Sum the per-block statistics (reduce_blocks, barebones :1033-1067, done on the host: B is small).
+static void reduce_stats(const std::vector<BlockStats>& bs, tb_stats* st, int* best_block) {
+  int best = -1; int best_bound = TBD_PINF; long long best_time = 0;
+  long long first_idle = -1;
+  for (size_t i = 0; i < bs.size(); ++i) {
+    const BlockStats& b = bs[i];
+    st->nodes += b.nodes; st->fails += b.fails; st->solutions += b.solutions;
+    st->depth_max = std::max(st->depth_max, b.depth_max);
+    st->exhaustive = st->exhaustive && b.exhaustive;
+    st->eps_solved_subproblems += b.eps_solved; st->eps_skipped_subproblems += b.eps_skipped;
+    st->num_blocks_done += b.blocks_done;
+    st->fixpoint_iterations += b.fixpoint_iterations; st->num_deductions += b.deductions;
+    st->bounds_narrowed += b.narrowed;
+    st->cumulative_time_block_ns += b.t_idle;
+    st->timers_ns[TB_TIMER_FIXPOINT] += b.t_fixpoint;
+    st->timers_ns[TB_TIMER_DIVE] += b.t_dive;
+    st->timers_ns[TB_TIMER_SEARCH] += b.t_idle - b.t_fixpoint;
+    if (first_idle < 0 || b.t_idle < first_idle) first_idle = b.t_idle;
+    if (b.has_best) {
+      if (best < 0 || b.best_bound < best_bound || (b.best_bound == best_bound && b.t_best <= best_time)) {
+        best = (int)i; best_bound = b.best_bound; best_time = b.t_best;
+      }
+    }
+  }
+  st->timers_ns[TB_TIMER_FIRST_BLOCK_IDLE] = std::max<long long>(first_idle, 0);
+  st->timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND] = best >= 0 ? best_time : 0;
+  if (best_block) *best_block = best;
+}
+
+static void unpack_store(const tb_solver* s, const int* img, int32_t* lb, int32_t* ub) {
+  const int vp = s->P.vpad;
+  for (int v = 0; v < s->nvars; ++v) {
+    if (s->aos) { lb[v] = img[2 * v]; ub[v] = img[2 * v + 1]; }
+    else { lb[v] = img[v]; ub[v] = img[vp + v]; }
+  }
+}
+
+static unsigned long long host_globaltimer_probe(tb_solver* s);
+
+__global__ void read_globaltimer_kernel(unsigned long long* out) { *out = globaltimer_ns(); }
+
+static unsigned long long host_globaltimer_probe(tb_solver* s) {
+  unsigned long long* d = (unsigned long long*)s->d_next;   // scratch: overwritten before every launch
+  read_globaltimer_kernel<<<1, 1, 0, s->stream>>>(d);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream);
+  cudaStreamSynchronize(s->stream);
+  return h;
+}
+
+static double now_ms() {
+  struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+  return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
+extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t* best_lb, int32_t* best_ub,
+                              int32_t* has_solution, int32_t* exhaustive, tb_stats* stats) {
+  if (!s) { set_error("null solver"); return TB_ERR_INVALID; }
+  CU(cudaSetDevice(s->device));
+  DevParams& P = s->P;
+  const double t_begin = now_ms();
+  tb_status rc;
+  if ((rc = reset_stats(s, s->num_blocks))) return rc;
+  P.t_start = host_globaltimer_probe(s);
+  const int pinf = TBD_PINF, zero = 0;
+  const unsigned long long first_free = (unsigned long long)s->num_blocks;
+  // the incumbent cell is only reset when no peer can have written to it yet
+  if (s->peer_cells.empty()) CU(cudaMemcpyAsync(s->d_bound, &pinf, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_next, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaEventRecord(s->ev_start, s->stream));
+  rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
+    solve_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>
+        <<<s->num_blocks, s->threads, s->shared_bytes, s->stream>>>(P);
+    CU(cudaGetLastError());
+    return TB_OK;
+  });
+  if (rc) return rc;
+  CU(cudaEventRecord(s->ev_stop, s->stream));
+  // wait_solving_ends (memory_gpu.hpp:174-196): poll stop / timeout, raise the device flag asynchronously
+  bool interrupted = false;
+  while (true) {
+    cudaError_t q = cudaEventQuery(s->ev_stop);
+    if (q == cudaSuccess) break;
+    if (q != cudaErrorNotReady) { set_error(std::string("kernel failed: ") + cudaGetErrorString(q)); return TB_ERR_CUDA; }
+    bool must = (stop_flag && *stop_flag) || (s->opt.timeout_ms && now_ms() - t_begin >= (double)s->opt.timeout_ms);
+    if (must && !interrupted) {
+      interrupted = true;
+      CU(cudaMemcpyAsync(s->d_stop, s->h_pinned_one, sizeof(int), cudaMemcpyHostToDevice, s->copy_stream));
+    }
+    struct timespec ts = {0, 200000};
+    nanosleep(&ts, nullptr);
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  float kms = 0.f;
+  CU(cudaEventElapsedTime(&kms, s->ev_start, s->ev_stop));
+  std::vector<BlockStats> bs((size_t)s->num_blocks);
+  CU(cudaMemcpy(bs.data(), P.stats, bs.size() * sizeof(BlockStats), cudaMemcpyDeviceToHost));
+  tb_stats st; memset(&st, 0, sizeof(st));
+  st.exhaustive = 1;
+  fill_config(s, &st);
+  int best_block = -1;
+  reduce_stats(bs, &st, &best_block);
+  for (auto& b : bs) if (b.error) { set_error("decision stack overflow (raise max_depth)"); rc = (tb_status)b.error; }
+  if (interrupted) st.exhaustive = 0;
+  st.kernel_ms = kms;
+  st.timers_ns[TB_TIMER_OVERALL] = (int64_t)((now_ms() - t_begin) * 1e6);
+  if (has_solution) *has_solution = best_block >= 0;
+  if (best_block >= 0 && best_lb && best_ub) {
+    std::vector<int> img((size_t)2 * P.vpad);
+    CU(cudaMemcpy(img.data(), P.block_best + (size_t)best_block * 2 * P.vpad, img.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    unpack_store(s, img.data(), best_lb, best_ub);
+  }
+  if (exhaustive) *exhaustive = st.exhaustive;
+  if (stats) *stats = st;
+  return rc;
+}
+
+static tb_status ensure_batch(tb_solver* s, size_t n) {
+  if (n <= s->batch_cap) return TB_OK;
+  tb_status rc;
+  size_t cap = std::max<size_t>(n, 1);
+  size_t cells = cap * (size_t)std::max(1, s->nvars);
+  if ((rc = dev_alloc(s, &s->d_in_lb, cells))) return rc;
+  if ((rc = dev_alloc(s, &s->d_in_ub, cells))) return rc;
+  if ((rc = dev_alloc(s, &s->d_out_lb, cells))) return rc;
+  if ((rc = dev_alloc(s, &s->d_out_ub, cells))) return rc;
+  if ((rc = dev_alloc(s, &s->d_out_i0, cap))) return rc;
+  if ((rc = dev_alloc(s, &s->d_out_i1, cap))) return rc;
+  s->batch_cap = cap;
+  return TB_OK;
+}
+
+extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int32_t* lb_in, const int32_t* ub_in,
+                                        int32_t* lb_out, int32_t* ub_out, int32_t* failed, tb_stats* stats) {
+  if (!s || nstores < 0) { set_error("invalid argument"); return TB_ERR_INVALID; }
+  if (nstores == 0) return TB_OK;
+  CU(cudaSetDevice(s->device));
+  tb_status rc;
+  if ((rc = ensure_batch(s, (size_t)nstores))) return rc;
+  const int grid = std::min(nstores, s->num_blocks);
+  if ((rc = reset_stats(s, grid))) return rc;
+  const size_t nv = (size_t)s->nvars, cells = nv * (size_t)nstores;
+  std::vector<int32_t> tmp;
+  const int32_t *hl = lb_in, *hu = ub_in;
+  if (!lb_in || !ub_in) {          // NULL = the root store, replicated
+    tmp.resize(2 * cells);
+    std::vector<int> img((size_t)2 * s->P.vpad);
+    CU(cudaMemcpy(img.data(), s->P.root_store, img.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> rl(nv), ru(nv);
+    unpack_store(s, img.data(), rl.data(), ru.data());
+    for (int b = 0; b < nstores; ++b) { std::copy(rl.begin(), rl.end(), tmp.begin() + b * nv); std::copy(ru.begin(), ru.end(), tmp.begin() + cells + b * nv); }
+    hl = tmp.data(); hu = tmp.data() + cells;
+  }
+  if (cells) {
+    CU(cudaMemcpyAsync(s->d_in_lb, hl, cells * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_in_ub, hu, cells * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  }
+  const int repeat = std::max(1, env_int("TB_PROPAGATE_REPEAT", 1));
+  CU(cudaEventRecord(s->ev_start, s->stream));
+  rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
+    propagate_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>
+        <<<grid, s->threads, s->shared_bytes, s->stream>>>(s->P, nstores, s->d_in_lb, s->d_in_ub, s->d_out_lb, s->d_out_ub, s->d_out_i0, repeat);
+    CU(cudaGetLastError());
+    return TB_OK;
+  });
+  if (rc) return rc;
+  CU(cudaEventRecord(s->ev_stop, s->stream));
+  if (cells && lb_out) CU(cudaMemcpyAsync(lb_out, s->d_out_lb, cells * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  if (cells && ub_out) CU(cudaMemcpyAsync(ub_out, s->d_out_ub, cells * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  if (failed) CU(cudaMemcpyAsync(failed, s->d_out_i0, (size_t)nstores * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (stats) {
+    float kms = 0.f;
+    CU(cudaEventElapsedTime(&kms, s->ev_start, s->ev_stop));
+    std::vector<BlockStats> bs((size_t)grid);
+    CU(cudaMemcpy(bs.data(), s->P.stats, bs.size() * sizeof(BlockStats), cudaMemcpyDeviceToHost));
+    memset(stats, 0, sizeof(*stats));
+    stats->exhaustive = 1;
+    fill_config(s, stats);
+    reduce_stats(bs, stats, nullptr);
+    stats->num_blocks = grid;
+    stats->kernel_ms = kms;
+  }
+  return TB_OK;
+}
+
+extern "C" tb_status tb_propagate(tb_solver* s, const int32_t* lb_in, const int32_t* ub_in, int32_t* lb_out, int32_t* ub_out,
+                                  int32_t* failed, tb_stats* stats) {
+  return tb_propagate_batch(s, 1, lb_in, ub_in, lb_out, ub_out, failed, stats);
+}
+
+extern "C" tb_status tb_dive_batch(tb_solver* s, uint64_t first, int32_t count, int32_t depth, int32_t* lb_out, int32_t* ub_out,
+                                   int32_t* remaining_depth, int32_t* leaf_kind) {
+  if (!s || count < 0 || depth < 0 || depth > 62) { set_error("invalid argument"); return TB_ERR_INVALID; }
+  if (count == 0) return TB_OK;
+  CU(cudaSetDevice(s->device));
+  tb_status rc;
+  if ((rc = ensure_batch(s, (size_t)count))) return rc;
+  const int grid = std::min(count, s->num_blocks);
+  if ((rc = reset_stats(s, grid))) return rc;
+  const int zero = 0, pinf = TBD_PINF;
+  CU(cudaMemcpyAsync(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  if (s->peer_cells.empty()) CU(cudaMemcpyAsync(s->d_bound, &pinf, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  DevParams P = s->P;
+  P.cutnodes = 0;
+  P.t_start = 0;
+  rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
+    dive_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>
+        <<<grid, s->threads, s->shared_bytes, s->stream>>>(P, first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1);
+    CU(cudaGetLastError());
+    return TB_OK;
+  });
+  if (rc) return rc;
+  const size_t cells = (size_t)s->nvars * (size_t)count;
+  if (cells && lb_out) CU(cudaMemcpyAsync(lb_out, s->d_out_lb, cells * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  if (cells && ub_out) CU(cudaMemcpyAsync(ub_out, s->d_out_ub, cells * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  if (remaining_depth) CU(cudaMemcpyAsync(remaining_depth, s->d_out_i0, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  if (leaf_kind) CU(cudaMemcpyAsync(leaf_kind, s->d_out_i1, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return TB_OK;
+}
+
+extern "C" tb_status tb_dive(tb_solver* s, uint64_t idx, int32_t depth, int32_t* lb_out, int32_t* ub_out,
+                             int32_t* remaining_depth, int32_t* leaf_kind) {
+  return tb_dive_batch(s, idx, 1, depth, lb_out, ub_out, remaining_depth, leaf_kind);
+}
+
+// ---- cross-GPU incumbent cells ---------------------------------------------------------------
+static tb_status publish_peers(tb_solver* s) {
+  if (s->peer_cells.empty()) { s->P.peer_bounds = nullptr; s->P.npeers = 0; return TB_OK; }
+  CU(cudaSetDevice(s->device));
+  int** d = nullptr;
+  tb_status rc = dev_alloc(s, &d, s->peer_cells.size());
+  if (rc) return rc;
+  CU(cudaMemcpy(d, s->peer_cells.data(), s->peer_cells.size() * sizeof(int*), cudaMemcpyHostToDevice));
+  s->P.peer_bounds = d; s->P.npeers = (int)s->peer_cells.size();
+  const int pinf = TBD_PINF;
+  CU(cudaMemcpy(s->d_bound, &pinf, sizeof(int), cudaMemcpyHostToDevice));
+  return TB_OK;
+}
+
+extern "C" tb_status tb_link_peers(tb_solver** solvers, int32_t n) {
+  if (!solvers || n <= 0) { set_error("invalid argument"); return TB_ERR_INVALID; }
+  for (int i = 0; i < n; ++i) {
+    tb_solver* a = solvers[i];
+    a->peer_cells.clear();
+    CU(cudaSetDevice(a->device));
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      tb_solver* b = solvers[j];
+      if (a->device != b->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, a->device, b->device));
+        if (!can) { set_error("devices cannot access each other's memory"); return TB_ERR_UNSUPPORTED; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return TB_ERR_CUDA; }
+        cudaGetLastError();
+      }
+      a->peer_cells.push_back(b->d_bound);
+    }
+  }
+  for (int i = 0; i < n; ++i) { tb_status rc = publish_peers(solvers[i]); if (rc) return rc; }
+  return TB_OK;
+}
+
+extern "C" tb_status tb_export_bound_handle(tb_solver* s, void* handle64) {
+  if (!s || !handle64) { set_error("null argument"); return TB_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  CU(cudaSetDevice(s->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, s->d_bound));
+  memcpy(handle64, &h, 64);
+  return TB_OK;
+}
+
+extern "C" tb_status tb_import_peer_bounds(tb_solver* s, const void* handles64, int32_t npeers) {
+  if (!s || (npeers && !handles64) || npeers < 0) { set_error("invalid argument"); return TB_ERR_INVALID; }
+  CU(cudaSetDevice(s->device));
+  s->peer_cells.clear();
+  for (int i = 0; i < npeers; ++i) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles64 + (size_t)i * 64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->ipc_opened.push_back(p);
+    s->peer_cells.push_back((int*)p);
+  }
+  return publish_peers(s);
+}
+
+extern "C" tb_status tb_read_bound(tb_solver* s, int32_t* bound) {
+  if (!s || !bound) { set_error("null argument"); return TB_ERR_INVALID; }
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpy(bound, s->d_bound, sizeof(int), cudaMemcpyDeviceToHost));
+  return TB_OK;
+}

@@ -1,0 +1,48 @@
+// engine_internal.h — POD structures shared between the host driver and the kernels.
+#pragma once
+#include <stdint.h>
+
+// One entry of the per-block decision stack: LightBranch<Itv>
+// (reference include/barebones_dive_and_solve.hpp:135,358-393). 32 bytes.
+struct Decision {
+  int var;
+  int clb0, cub0, clb1, cub1;   // children[0], children[1]
+  int rope0, rope1;             // ropes[0], ropes[1]
+  int cur;                      // current_idx
+};
+
+struct DevStrategy {            // StrategyType (barebones :84)
+  int var_order, val_order, n;
+  const int* vars;              // device pointer; n == 0 -> all store variables
+};
+
+// Per-block statistics: Statistics<> fields written on the device (include/statistics.hpp:137-154).
+struct BlockStats {
+  unsigned long long nodes, fails, solutions, eps_solved, eps_skipped, blocks_done;
+  unsigned long long fixpoint_iterations, deductions, narrowed;
+  long long t_fixpoint, t_dive, t_best, t_idle;
+  int depth_max, exhaustive, best_bound, has_best, error, pad_;
+};
+
+// Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
+// flattened to plain device pointers (no managed memory, no device-side malloc).
+struct DevParams {
+  int nvars, vpad, nprops, nprops_pad;
+  const void* props;            // packed u64 or int4 table, padded with NOPs to a multiple of 32
+  const int* root_store;        // image of the root store, same layout as a block store
+  int nstrategies, has_eps_strategy, obj_var, fixpoint_kind, wac1_threshold, subproblems_power;
+  const DevStrategy* strategies;
+  unsigned long long num_subproblems, cutnodes, t_start;
+  int rank, world, max_depth, npeers;
+  // per-block scratch in global memory, [slot] major
+  int* block_root;              // snapshot of the subproblem root (root_store, barebones :89)
+  int* block_best;              // best solution of the block (best_store, :92)
+  int* block_store;             // current store when it does not live in shared memory
+  Decision* decisions;
+  BlockStats* stats;
+  // grid-shared cells
+  unsigned long long* next_subproblem;   // GridData::next_subproblem (:418), counts this GPU's shard
+  int* appx_best_bound;                  // GridData::appx_best_bound (:426), this GPU's copy
+  int* const* peer_bounds;               // the other GPUs' copies (peer-mapped over NVLink)
+  volatile int* stop;                    // UnifiedData::stop (:64), raised by the host with an async copy
+};

@@ -1,0 +1,178 @@
+"""ctypes binding of turbo_b200/libturbo_b200.so (the product's C ABI, include/turbo_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible when a
+solver is created, this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libturbo_b200.so")
+_LIB = None
+
+
+class TurboError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{abi.STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C turbo_b200`). The engine has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        i32p = C.POINTER(C.c_int32)
+        vp = C.c_void_p
+        L.tb_create.argtypes = [C.POINTER(vp), C.POINTER(abi.TbProblem), C.POINTER(abi.TbOptions)]
+        L.tb_propagate.argtypes = [vp, i32p, i32p, i32p, i32p, i32p, C.POINTER(abi.TbStats)]
+        L.tb_propagate_batch.argtypes = [vp, C.c_int32, i32p, i32p, i32p, i32p, i32p, C.POINTER(abi.TbStats)]
+        L.tb_dive.argtypes = [vp, C.c_uint64, C.c_int32, i32p, i32p, i32p, i32p]
+        L.tb_dive_batch.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p]
+        L.tb_solve.argtypes = [vp, i32p, i32p, i32p, i32p, i32p, C.POINTER(abi.TbStats)]
+        L.tb_link_peers.argtypes = [C.POINTER(vp), C.c_int32]
+        L.tb_export_bound_handle.argtypes = [vp, vp]
+        L.tb_import_peer_bounds.argtypes = [vp, vp, C.c_int32]
+        L.tb_read_bound.argtypes = [vp, i32p]
+        L.tb_get_config.argtypes = [vp, C.POINTER(abi.TbStats)]
+        L.tb_destroy.argtypes = [vp]
+        L.tb_destroy.restype = None
+        L.tb_last_error.restype = C.c_char_p
+        L.tb_version.restype = C.c_char_p
+        L.tb_device_count.restype = C.c_int32
+        for name in ("tb_create", "tb_propagate", "tb_propagate_batch", "tb_dive", "tb_dive_batch", "tb_solve",
+                     "tb_link_peers", "tb_export_bound_handle", "tb_import_peer_bounds", "tb_read_bound",
+                     "tb_get_config"):
+            getattr(L, name).restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise TurboError(rc, lib().tb_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def device_count():
+    return int(lib().tb_device_count())
+
+
+class Solver:
+    """One engine instance bound to one CUDA device (tb_solver)."""
+
+    def __init__(self, problem, **options):
+        self.problem = problem
+        self.options = abi.default_options(**options)
+        self._h = C.c_void_p()
+        _check(lib().tb_create(C.byref(self._h), C.byref(problem.c), C.byref(self.options)))
+
+    def close(self):
+        if self._h:
+            lib().tb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def config(self):
+        st = abi.TbStats()
+        _check(lib().tb_get_config(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def propagate(self, lb=None, ub=None):
+        n = self.problem.nvars
+        if lb is not None:
+            lb = np.ascontiguousarray(lb, dtype=np.int32)
+            ub = np.ascontiguousarray(ub, dtype=np.int32)
+        olb = np.zeros(max(1, n), np.int32)
+        oub = np.zeros(max(1, n), np.int32)
+        failed = C.c_int32(0)
+        st = abi.TbStats()
+        _check(lib().tb_propagate(self._h, _p(lb), _p(ub), _p(olb), _p(oub), C.byref(failed), C.byref(st)))
+        return dict(lb=olb[:n], ub=oub[:n], failed=bool(failed.value), stats=st.as_dict())
+
+    def propagate_batch(self, lb, ub):
+        lb = np.ascontiguousarray(lb, dtype=np.int32)
+        ub = np.ascontiguousarray(ub, dtype=np.int32)
+        b = lb.shape[0]
+        olb = np.zeros_like(lb)
+        oub = np.zeros_like(ub)
+        failed = np.zeros(b, np.int32)
+        st = abi.TbStats()
+        _check(lib().tb_propagate_batch(self._h, b, _p(lb), _p(ub), _p(olb), _p(oub), _p(failed), C.byref(st)))
+        return dict(lb=olb, ub=oub, failed=failed.astype(bool), stats=st.as_dict())
+
+    def dive_batch(self, first, count, depth):
+        n = self.problem.nvars
+        olb = np.zeros((count, max(1, n)), np.int32)
+        oub = np.zeros((count, max(1, n)), np.int32)
+        if n:
+            olb = np.zeros((count, n), np.int32)
+            oub = np.zeros((count, n), np.int32)
+        rem = np.zeros(count, np.int32)
+        kind = np.zeros(count, np.int32)
+        _check(lib().tb_dive_batch(self._h, first, count, depth, _p(olb), _p(oub), _p(rem), _p(kind)))
+        return dict(lb=olb, ub=oub, remaining_depth=rem, leaf_kind=kind)
+
+    def dive(self, idx, depth):
+        r = self.dive_batch(idx, 1, depth)
+        return dict(lb=r["lb"][0], ub=r["ub"][0], remaining_depth=int(r["remaining_depth"][0]),
+                    leaf_kind=int(r["leaf_kind"][0]))
+
+    def solve(self, stop_flag=None):
+        n = max(1, self.problem.nvars)
+        lb = np.zeros(n, np.int32)
+        ub = np.zeros(n, np.int32)
+        has = C.c_int32(0)
+        exh = C.c_int32(0)
+        st = abi.TbStats()
+        _check(lib().tb_solve(self._h, stop_flag, _p(lb), _p(ub), C.byref(has), C.byref(exh), C.byref(st)))
+        obj = None
+        if has.value and self.problem.obj_var >= 0:
+            obj = int(lb[self.problem.obj_var])
+        return dict(lb=lb[:self.problem.nvars], ub=ub[:self.problem.nvars], has_solution=bool(has.value),
+                    exhaustive=bool(exh.value), objective=obj, stats=st.as_dict())
+
+    def export_bound_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(lib().tb_export_bound_handle(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def import_peer_bounds(self, handles):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().tb_import_peer_bounds(self._h, C.cast(buf, C.c_void_p), len(handles)))
+
+    def read_bound(self):
+        v = C.c_int32(0)
+        _check(lib().tb_read_bound(self._h, C.byref(v)))
+        return v.value
+
+
+def link_peers(solvers):
+    arr = (C.c_void_p * len(solvers))(*[s.handle for s in solvers])
+    _check(lib().tb_link_peers(arr, len(solvers)))
