@@ -185,6 +185,10 @@ tb_status tb_model_synthetic(tb_model** out, int32_t nvars, int32_t nprops, uint
 tb_status tb_model_load_tnf(tb_model** out, const char* path);
 tb_status tb_model_save_tnf(const tb_model*, const char* path);
 
+/* Prepend the EPS strategy used while diving (-eps_var_order / -eps_value_order,
+ * push_eps_strategy, common_solving.hpp:652-667). The tb_problem must be re-read afterwards. */
+tb_status tb_model_push_eps_strategy(tb_model*, int32_t var_order, int32_t val_order);
+
 const tb_problem* tb_model_problem(const tb_model*);
 /* 1 when the FlatZinc model maximises (the TNF minimises __MINIMIZE_OBJ = -x, common_solving.hpp:489-510),
  * 0 minimise, -1 satisfy. */
