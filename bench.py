@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the dive-and-solve hot path (BASELINE.json metric: propagations/s and
+search nodes/s), measured through the C ABI of libturbo_b200.so.
+
+A *step* is one bounded dive-and-solve pass (`tb_solve` with a per-block node budget, the
+reference's `-cutnodes`) over the trains15 TNF network (BASELINE config 2, the configuration the
+metric is quoted on; fixture tests/golden/trains15.npz produced by our front-end from
+benchmarks/trains15.fzn).  `value` counts propagations (one evaluation of one TNF propagator,
+the reference's `num_deductions`, include/statistics.hpp:151,354) over the device time of the solve
+kernel with the network already resident in HBM; `e2e` runs the same step from host buffers
+through tb_create + tb_solve + result read-back + tb_destroy.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+N > 1 is launched under torchrun (one rank per GPU): subproblems are sharded idx = k*N + rank, the
+incumbent is exchanged through CUDA-IPC peer-mapped cells, torch.distributed only carries the
+handles and the final reduction.  `--impl reference` times the CPU oracle (the reference itself
+cannot be built offline: its arithmetic lives in un-vendored lala-* libraries).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import golden_io  # noqa: E402  (fixture loader only; no oracle code)
+from turbo_b200 import abi  # noqa: E402
+
+SM_COUNT = 148
+SMEM_BYTES_PER_CLK_PER_SM = 128           # B300_MICROARCH.md "smem crossbar BW 128/N B/cyc/SM"
+
+
+def load_workload(name):
+    if name.startswith("synthetic"):
+        from turbo_b200.model import Model
+        _, nv, npr = name.split(":") if ":" in name else (name, "100000", "1000000")
+        m = Model.synthetic(int(nv), int(npr), 0xB200)
+        return m.problem, dict(objective_kind=-1)
+    return golden_io.load(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        clocks, maxs, reasons = [], [], set()
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clocks.append(float(f[1]))
+                maxs.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if clocks:
+            out.update(sm_mhz=float(np.median(clocks)), sm_max_mhz=float(max(maxs)), reasons=sorted(reasons), samples=len(clocks))
+        return out
+
+
+def problem_bytes(pb):
+    return int(pb.lb.nbytes + pb.ub.nbytes + pb.props.nbytes + sum(v.nbytes for _, _, v in pb.strategies))
+
+
+def run_ours(args):
+    import torch
+    from turbo_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if engine.device_count() <= 0:
+        raise SystemExit("no CUDA device: bench.py measures the CUDA engine and has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pb, info = load_workload(args.workload)
+    opts = dict(device=local, gpu_rank=rank, gpu_world=world, cutnodes=args.cutnodes,
+                fixpoint=abi.FP_AC1 if args.fp == "ac1" else abi.FP_WAC1)
+    if args.tpb:
+        opts["threads_per_block"] = args.tpb
+    if args.blocks:
+        opts["or_blocks"] = args.blocks
+    solver = engine.Solver(pb, **opts)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, solver.export_bound_handle())
+        solver.import_peer_bounds([h for r, h in enumerate(handles) if r != rank])
+    cfg = solver.config()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        flush.fill_(1)                       # evict L2 between steps
+        torch.cuda.synchronize()
+        return solver.solve()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    kernel_ms, ded, nodes, narrowed, fp_ns, launches = 0.0, 0, 0, 0, 0, 0
+    last = None
+    for _ in range(args.steps):
+        r = step()
+        st = r["stats"]
+        kernel_ms += st["kernel_ms"]
+        ded += st["num_deductions"]
+        nodes += st["nodes"]
+        narrowed += st["bounds_narrowed"]
+        fp_ns += st["timers_ns"][abi.TIMER_FIXPOINT]
+        launches += 2                        # solve_kernel + the 1-thread globaltimer probe
+        last = r
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- e2e: host buffers -> tb_create (H2D) -> tb_solve -> results (D2H) -> tb_destroy -------------------
+    e2e_ded, e2e_s = 0, 0.0
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    for _ in range(e2e_steps):
+        t = time.perf_counter()
+        with engine.Solver(pb, **opts) as s2:
+            if world > 1:
+                pass                         # the e2e leg measures the per-GPU drop-in call; bounds stay local
+            r2 = s2.solve()
+        e2e_s += time.perf_counter() - t
+        e2e_ded += r2["stats"]["num_deductions"]
+    h2d = problem_bytes(pb)
+    d2h = int(2 * 4 * pb.nvars + abi.C.sizeof(abi.TbStats) + 120 * cfg["num_blocks"])
+
+    # ---- reduce over ranks: sums of counters, max of times ---------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([ded, nodes, narrowed, e2e_ded], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ded, nodes, narrowed, e2e_ded = (float(x) for x in t.tolist())
+        m = torch.tensor([kernel_ms, e2e_s, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        kernel_ms, e2e_s, wall_s = (float(x) for x in m.tolist())
+
+    line = None
+    if rank == 0:
+        secs = kernel_ms / 1e3
+        sm_mhz = clocks["sm_mhz"] or 0.0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        smem_bytes = 24.0 * ded + 4.0 * narrowed          # algorithmic bytes per propagation
+        achieved = smem_bytes / secs / 1e9 if secs > 0 else 0.0
+        clk_for_peak = sm_mhz if sm_mhz > 0 else float(peaks.get("sm_max_mhz", 1965.0))
+        peak = SMEM_BYTES_PER_CLK_PER_SM * SM_COUNT * world * clk_for_peak * 1e6 / 1e9
+        line = {
+            "metric": "propagations/sec", "value": ded / secs if secs > 0 else 0.0, "unit": "propagations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic"
+            if args.workload.startswith("synthetic") else "tests/golden fixture (TNF of the reference's benchmarks/%s.fzn)" % args.workload,
+            "config": {"workload": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "cutnodes_per_block": args.cutnodes,
+                       "fixpoint": args.fp, "num_blocks_per_gpu": cfg["num_blocks"], "threads_per_block": cfg["threads_per_block"],
+                       "memory_configuration": abi.MEM_NAMES.get(cfg["mem_kind"], "?"), "subproblems_power": cfg["subproblems_power"],
+                       "l2": "flushed between steps (256 MiB write)", "parallelism": f"eps-shard x{world}"},
+            "nodes_per_sec": nodes / secs if secs > 0 else 0.0,
+            "nodes": nodes, "propagations": ded, "bounds_narrowed": narrowed,
+            "wall_ms_per_step": wall_s * 1e3 / args.steps,
+            "fixpoint_time_share": (fp_ns / 1e6 / max(1, cfg["num_blocks"])) / kernel_ms if kernel_ms > 0 else None,
+            "best_objective": (golden_io.user_objective(info, last["lb"], last["ub"]) if last["has_solution"] and info.get("objective_kind", -1) >= 0 else None),
+            "e2e": {"value": e2e_ded / e2e_s if e2e_s > 0 else 0.0, "unit": "propagations/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "roofline": {"bound": "smem", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "kernel": "solve_kernel (persistent dive-and-solve; fixpoint loop inside)",
+                         "peak_source": "128 B/clk/SM x 148 SMs x SM clock sampled under load (shared-memory roofline, SURVEY.md 8d)",
+                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(pb, cfg["subproblems_power"], args)
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(pb, depth, args, seconds=8.0):
+    """The CPU oracle (kind "port") on the host cores, on a bounded sample of the same workload."""
+    from oracle import oracle_py as orc
+    depth = min(depth, 20)
+    cores = os.cpu_count() or 1
+    t = time.perf_counter()
+    r1 = orc.solve(pb, depth=depth, timeout_ms=int(seconds * 1000), nthreads=1)
+    s1 = time.perf_counter() - t
+    t = time.perf_counter()
+    rn = orc.solve(pb, depth=depth, timeout_ms=int(seconds * 1000), nthreads=cores)
+    sn = time.perf_counter() - t
+    return {"value": rn["stats"]["num_deductions"] / sn, "unit": "propagations/s", "cores": cores, "kind": "port",
+            "sample": f"oracle dive-and-solve on the same TNF for {seconds:.0f} s (Gauss-Seidel AC1, EPS over {cores} threads)",
+            "nodes_per_sec": rn["stats"]["nodes"] / sn,
+            "value_1core": r1["stats"]["num_deductions"] / s1, "nodes_per_sec_1core": r1["stats"]["nodes"] / s1}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path. The reference cannot be built here (un-vendored
+    lala-* dependencies), so this times the oracle port with all host threads, bounded per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as orc
+    pb, info = load_workload(args.workload)
+    cores = os.cpu_count() or 1
+    depth = 12
+    budget_ms = 4000
+    for _ in range(min(args.warmup, 1)):
+        orc.solve(pb, depth=depth, timeout_ms=500, nthreads=cores)
+    ded, nodes, secs = 0, 0, 0.0
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        r = orc.solve(pb, depth=depth, timeout_ms=budget_ms, nthreads=cores)
+        secs += time.perf_counter() - t
+        ded += r["stats"]["num_deductions"]
+        nodes += r["stats"]["nodes"]
+    value = ded / secs
+    line = {"impl": "reference", "metric": "propagations/sec", "value": value, "unit": "propagations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "tests/golden fixture (TNF of the reference's benchmarks/%s.fzn)" % args.workload,
+            "config": {"workload": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "step": f"{budget_ms} ms of CPU dive-and-solve"},
+            "nodes_per_sec": nodes / secs,
+            "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x {budget_ms} ms of oracle dive-and-solve, EPS over {cores} threads"},
+            "e2e": {"value": value, "unit": "propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="trains15")
+    ap.add_argument("--cutnodes", type=int, default=2000)
+    ap.add_argument("--fp", default="wac1", choices=["ac1", "wac1"])
+    ap.add_argument("--tpb", type=int, default=0)
+    ap.add_argument("--blocks", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
