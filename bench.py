@@ -225,6 +225,11 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pb, cfg["subproblems_power"], args)
     solver.close()
+    if rank == 0 and world == 1 and not args.no_fixpoint_leg:
+        # the fixpoint kernel alone (the kernel SURVEY.md 8(d)'s shared-memory roofline is stated for)
+        from tools.fixpoint_bench import measure
+        line["fixpoint_kernel"] = measure(pb, repeat=20, fp=args.fp, tpb=args.tpb, blocks=args.blocks, device=local,
+                                          sm_mhz=clocks["sm_mhz"])
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -294,6 +299,7 @@ def main():
     ap.add_argument("--tpb", type=int, default=0)
     ap.add_argument("--blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fixpoint-leg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

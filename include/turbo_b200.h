@@ -85,7 +85,7 @@ typedef struct {
   int32_t max_depth;            /* decision stack capacity; 0 = 10000 (MAX_SEARCH_DEPTH, :14) */
   int32_t gpu_rank, gpu_world;  /* subproblem shard of this solver: idx = k * world + rank; 0/0 or 0/1 = all */
   int32_t device;               /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t propagate_repeat;    /* tb_propagate_batch re-runs each store this many times (throughput runs); 0 = 1 */
   uint64_t timeout_ms;          /* -t; 0 = none (enforced by the caller through stop_flag and here) */
   uint64_t cutnodes;            /* -cutnodes; 0 = none (per block, barebones :1024) */
   uint64_t seed;

@@ -54,7 +54,7 @@ class TbOptions(C.Structure):
                 ("mem_kind", C.c_int32), ("cluster_size", C.c_int32),
                 ("verbose", C.c_int32), ("max_depth", C.c_int32),
                 ("gpu_rank", C.c_int32), ("gpu_world", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32),
+                ("device", C.c_int32), ("propagate_repeat", C.c_int32),
                 ("timeout_ms", C.c_uint64), ("cutnodes", C.c_uint64), ("seed", C.c_uint64)]
 
 

@@ -121,31 +121,50 @@ struct StoreRef {
   }
 };
 
+struct RawProp { unsigned long long w; int4 q; };
+
 template <bool PACKED>
-__device__ __forceinline__ void load_prop(const void* props, int i, int& op, int& x, int& y, int& z, bool in_smem) {
+__device__ __forceinline__ RawProp load_raw(const void* props, int i, bool in_smem) {
+  RawProp r;
+  if (PACKED) r.w = in_smem ? ((const unsigned long long*)props)[i] : __ldg((const unsigned long long*)props + i);
+  else r.q = in_smem ? ((const int4*)props)[i] : __ldg((const int4*)props + i);
+  return r;
+}
+template <bool PACKED>
+__device__ __forceinline__ void decode_raw(const RawProp& r, int& op, int& x, int& y, int& z) {
   if (PACKED) {
-    unsigned long long w = in_smem ? ((const unsigned long long*)props)[i] : __ldg((const unsigned long long*)props + i);
-    op = (int)(w >> 60); x = (int)((w >> 40) & 0xFFFFFu); y = (int)((w >> 20) & 0xFFFFFu); z = (int)(w & 0xFFFFFu);
-  } else {
-    int4 w = in_smem ? ((const int4*)props)[i] : __ldg((const int4*)props + i);
-    op = w.x; x = w.y; y = w.z; z = w.w;
-  }
+    const unsigned hi = (unsigned)(r.w >> 32), lo = (unsigned)r.w;
+    op = (int)(hi >> 28); x = (int)((hi >> 8) & 0xFFFFFu); y = (int)(((hi & 0xFFu) << 12) | (lo >> 20)); z = (int)(lo & 0xFFFFFu);
+  } else { op = r.q.x; x = r.q.y; y = r.q.z; z = r.q.w; }
 }
 
-// One evaluation of one propagator: 6 loads, candidates in registers, publish what narrows.
+// One evaluation of one propagator: 6 loads, new bounds in registers, publish only what narrowed.
+// In the steady state nothing narrows, so the common path is loads + arithmetic + one predicate.
 template <class Store>
 __device__ __forceinline__ int deduce(const Store& s, int op, int x, int y, int z, unsigned& narrowed) {
   int xl, xu, yl, yu, zl, zu;
   s.ld(x, xl, xu); s.ld(y, yl, yu); s.ld(z, zl, zu);
   if ((xl > xu) | (yl > yu) | (zl > zu)) return F_FAILED | F_NOT_ENTAILED;
-  tbd::Cand c;
-  int bits = tbd::eval(op, xl, xu, yl, yu, zl, zu, c);
-  if (c.xl > xl) { s.tell_lb(x, c.xl); bits |= F_CHANGED | (c.xl > xu ? F_FAILED : 0); ++narrowed; }
-  if (c.xu < xu) { s.tell_ub(x, c.xu); bits |= F_CHANGED | (c.xu < xl ? F_FAILED : 0); ++narrowed; }
-  if (c.yl > yl) { s.tell_lb(y, c.yl); bits |= F_CHANGED | (c.yl > yu ? F_FAILED : 0); ++narrowed; }
-  if (c.yu < yu) { s.tell_ub(y, c.yu); bits |= F_CHANGED | (c.yu < yl ? F_FAILED : 0); ++narrowed; }
-  if (c.zl > zl) { s.tell_lb(z, c.zl); bits |= F_CHANGED | (c.zl > zu ? F_FAILED : 0); ++narrowed; }
-  if (c.zu < zu) { s.tell_ub(z, c.zu); bits |= F_CHANGED | (c.zu < zl ? F_FAILED : 0); ++narrowed; }
+  int nxl = xl, nxu = xu, nyl = yl, nyu = yu, nzl = zl, nzu = zu;
+  bool entailed;
+  if (!tbd::is_rare(op)) entailed = tbd::hot_eval(op, xl, xu, yl, yu, zl, zu, nxl, nxu, nyl, nyu, nzl, nzu);
+  else {
+    tbd::Cand c;
+    tbd::rare_eval(op, xl, xu, yl, yu, zl, zu, &c);
+    nxl = max(xl, c.xl); nxu = min(xu, c.xu); nyl = max(yl, c.yl); nyu = min(yu, c.yu); nzl = max(zl, c.zl); nzu = min(zu, c.zu);
+    entailed = (xl == xu) & (yl == yu) & (zl == zu);
+  }
+  int bits = entailed ? 0 : F_NOT_ENTAILED;
+  if ((nxl != xl) | (nxu != xu) | (nyl != yl) | (nyu != yu) | (nzl != zl) | (nzu != zu)) {
+    bits |= F_CHANGED;
+    if (nxl != xl) { s.tell_lb(x, nxl); ++narrowed; }
+    if (nxu != xu) { s.tell_ub(x, nxu); ++narrowed; }
+    if (nyl != yl) { s.tell_lb(y, nyl); ++narrowed; }
+    if (nyu != yu) { s.tell_ub(y, nyu); ++narrowed; }
+    if (nzl != zl) { s.tell_lb(z, nzl); ++narrowed; }
+    if (nzu != zu) { s.tell_ub(z, nzu); ++narrowed; }
+    if ((nxl > nxu) | (nyl > nyu) | (nzl > nzu)) bits |= F_FAILED;
+  }
   return bits;
 }
 
@@ -211,9 +230,14 @@ struct Ctx {
     for (;; ++it) {
       int bits = 0;
       if (wac1) {
-        for (int base = tid - lane; base < n; base += T) {
+        // each warp owns chunks of 32 consecutive propagators; the next chunk's words are prefetched
+        // while the current chunk iterates to its warp-local fixpoint
+        int base = tid - lane;
+        RawProp cur = base < n ? load_raw<PACKED>(props, base + lane, props_in_smem) : RawProp{};
+        for (; base < n; base += T) {
+          const RawProp nxt = base + T < n ? load_raw<PACKED>(props, base + T + lane, props_in_smem) : RawProp{};
           int op, x, y, z;
-          load_prop<PACKED>(props, base + lane, op, x, y, z, props_in_smem);
+          decode_raw<PACKED>(cur, op, x, y, z);
           int b, wsticky = 0;          // wsticky is warp-uniform: every exit below is taken by the whole warp
           bool again;
           do {
@@ -226,12 +250,17 @@ struct Ctx {
           } while (again);
           bits |= (wsticky & (F_CHANGED | F_FAILED)) | (b & F_NOT_ENTAILED);
           if (wsticky & F_FAILED) break;
+          cur = nxt;
         }
       } else {
-        for (int i = tid; i < n; i += T) {
+        int i = tid;
+        RawProp cur = i < n ? load_raw<PACKED>(props, i, props_in_smem) : RawProp{};
+        for (; i < n; i += T) {
+          const RawProp nxt = i + T < n ? load_raw<PACKED>(props, i + T, props_in_smem) : RawProp{};
           int op, x, y, z;
-          load_prop<PACKED>(props, i, op, x, y, z, props_in_smem);
+          decode_raw<PACKED>(cur, op, x, y, z);
           bits |= deduce(store, op, x, y, z, narrowed);
+          cur = nxt;
         }
       }
       bits = __reduce_or_sync(0xffffffffu, bits);
@@ -873,10 +902,18 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (cudaMemcpy(d, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D root store"); return fail(TB_ERR_CUDA); }
     P.root_store = d;
   }
+  // Layout of the propagator table: inside every window of `threads` consecutive propagators (the ones
+  // a block evaluates concurrently in one step of a sweep) group equal operators together so that a
+  // warp's 32 lanes mostly run the same operator. The fixpoint does not depend on the order.
+  std::vector<tb_prop> ordered(pb->props, pb->props + pb->nprops);
+  if (env_int("TB_NO_OP_GROUPING", 0) == 0)
+    for (size_t w0 = 0; w0 < ordered.size(); w0 += (size_t)s->threads)
+      std::stable_sort(ordered.begin() + w0, ordered.begin() + std::min(ordered.size(), w0 + (size_t)s->threads),
+                       [](const tb_prop& a, const tb_prop& b) { return a.op < b.op; });
   if (s->packed) {
     std::vector<unsigned long long> w((size_t)P.nprops_pad, (unsigned long long)TB_OP_NOP << 60);
     for (int i = 0; i < pb->nprops; ++i) {
-      const tb_prop& p = pb->props[i];
+      const tb_prop& p = ordered[i];
       w[i] = ((unsigned long long)p.op << 60) | ((unsigned long long)p.x << 40) | ((unsigned long long)p.y << 20) | (unsigned long long)p.z;
     }
     unsigned long long* d = nullptr;
@@ -885,7 +922,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     P.props = d;
   } else {
     std::vector<tb_prop> w((size_t)P.nprops_pad, tb_prop{TB_OP_NOP, 0, 0, 0});
-    for (int i = 0; i < pb->nprops; ++i) w[i] = pb->props[i];
+    for (int i = 0; i < pb->nprops; ++i) w[i] = ordered[i];
     tb_prop* d = nullptr;
     if ((rc = dev_alloc(s, &d, w.size()))) return fail(rc);
     if (w.size() && cudaMemcpy(d, w.data(), w.size() * sizeof(tb_prop), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
@@ -1131,7 +1168,7 @@ extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int
     CU(cudaMemcpyAsync(s->d_in_lb, hl, cells * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->d_in_ub, hu, cells * sizeof(int), cudaMemcpyHostToDevice, s->stream));
   }
-  const int repeat = std::max(1, env_int("TB_PROPAGATE_REPEAT", 1));
+  const int repeat = std::max(1, s->opt.propagate_repeat);
   CU(cudaEventRecord(s->ev_start, s->stream));
   rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
     propagate_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>

@@ -85,7 +85,7 @@ __device__ __forceinline__ void quot(int pl, int pu, int dl, int du, int& ql, in
 }
 
 // ---- x = y * z ---------------------------------------------------------------------------------
-__device__ __noinline__ void mul(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
+__device__ __forceinline__ void mul(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
   if (fin(yl, yu) && fin(zl, zu)) {
     long long a = (long long)yl * zl, b = (long long)yl * zu, d = (long long)yu * zl, e = (long long)yu * zu;
     c.xl = clamp64(min4(a, b, d, e));
@@ -115,7 +115,7 @@ __device__ __noinline__ void mul(int xl, int xu, int yl, int yu, int zl, int zu,
 }
 
 // ---- x = y tdiv z, z != 0 ----------------------------------------------------------------------
-__device__ __noinline__ void tdiv(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
+__device__ __forceinline__ void tdiv(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
   if (zl == 0) { c.zl = 1; zl = 1; }
   if (zu == 0) { c.zu = -1; zu = -1; }
   if (zl > zu) return;
@@ -146,7 +146,7 @@ __device__ __noinline__ void tdiv(int xl, int xu, int yl, int yu, int zl, int zu
 }
 
 // ---- x = y tmod z, z != 0 ----------------------------------------------------------------------
-__device__ __noinline__ void tmod(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
+__device__ __forceinline__ void tmod(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
   (void)xl; (void)xu;
   if (zl == 0) { c.zl = 1; zl = 1; }
   if (zu == 0) { c.zu = -1; zu = -1; }
@@ -166,70 +166,75 @@ __device__ __noinline__ void tmod(int xl, int xu, int yl, int yu, int zl, int zu
   c.xl = lo; c.xu = hi;
 }
 
-// Evaluate propagator `op` on the loaded snapshot. Returns F_NOT_ENTAILED if `ask` is false.
-__device__ __forceinline__ int eval(int op, int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
+// The rare operators (MUL / TDIV / TMOD): kept out of line so that the hot loop stays small and
+// register-resident; candidates come back through one by-value struct.
+__device__ __noinline__ void rare_eval(int op, int xl, int xu, int yl, int yu, int zl, int zu, Cand* out) {
+  Cand c;
   c.xl = TBD_NINF; c.xu = TBD_PINF; c.yl = TBD_NINF; c.yu = TBD_PINF; c.zl = TBD_NINF; c.zu = TBD_PINF;
-  bool entailed;
-  switch (op) {
-    case TB_OP_ADD:
-      add(xl, xu, yl, yu, zl, zu, c);
-      entailed = (xl == xu) & (yl == yu) & (zl == zu);
-      break;
-    case TB_OP_LEQ:
-      if (xl >= 1) { c.yu = zu; c.zl = yl; entailed = yu <= zl; }
-      else if (xu <= 0) { c.yl = succ(zl); c.zu = pred(yu); entailed = yl > zu; }
-      else {
-        if (yu <= zl) c.xl = 1; else if (yl > zu) c.xu = 0;
-        entailed = false;
-      }
-      break;
-    case TB_OP_EQ:
-      if (xl >= 1) {
-        c.yl = zl; c.yu = zu; c.zl = yl; c.zu = yu;
-        entailed = (yl == yu) & (zl == zu) & (yl == zl);
-      }
-      else if (xu <= 0) {
-        if (yl == yu && fin(yl, yu)) { if (zl == yl) c.zl = yl + 1; if (zu == yl) c.zu = yl - 1; }
-        if (zl == zu && fin(zl, zu)) { if (yl == zl) c.yl = zl + 1; if (yu == zl) c.yu = zl - 1; }
-        entailed = (yu < zl) | (zu < yl);
-      }
-      else {
-        if (yu < zl || zu < yl) c.xu = 0;
-        else if (yl == yu && zl == zu && yl == zl) c.xl = 1;
-        entailed = false;
-      }
-      break;
-    case TB_OP_MIN:
-      c.xl = min(yl, zl); c.xu = min(yu, zu);
-      c.yl = xl; c.zl = xl;
-      if (yl > xu) c.zu = xu;
-      if (zl > xu) c.yu = xu;
-      entailed = (xl == xu) & (yl == yu) & (zl == zu);
-      break;
-    case TB_OP_MAX:
-      c.xl = max(yl, zl); c.xu = max(yu, zu);
-      c.yu = xu; c.zu = xu;
-      if (yu < xl) c.zl = xl;
-      if (zu < xl) c.yl = xl;
-      entailed = (xl == xu) & (yl == yu) & (zl == zu);
-      break;
-    case TB_OP_MUL:
-      mul(xl, xu, yl, yu, zl, zu, c);
-      entailed = (xl == xu) & (yl == yu) & (zl == zu);
-      break;
-    case TB_OP_TDIV:
-      tdiv(xl, xu, yl, yu, zl, zu, c);
-      entailed = (xl == xu) & (yl == yu) & (zl == zu);
-      break;
-    case TB_OP_TMOD:
-      tmod(xl, xu, yl, yu, zl, zu, c);
-      entailed = (xl == xu) & (yl == yu) & (zl == zu);
-      break;
-    default:  // TB_OP_NOP
-      entailed = true;
-      break;
-  }
-  return entailed ? 0 : F_NOT_ENTAILED;
+  if (op == TB_OP_MUL) mul(xl, xu, yl, yu, zl, zu, c);
+  else if (op == TB_OP_TDIV) tdiv(xl, xu, yl, yu, zl, zu, c);
+  else tmod(xl, xu, yl, yu, zl, zu, c);
+  *out = c;
 }
+
+// Hot operators, fully inlined. On entry n* hold the current bounds; on exit the narrowed ones
+// (new = current meet candidate). Returns whether the propagator is entailed on the snapshot.
+// `op` must be one of ADD, LEQ, EQ, MIN, MAX, NOP.
+__device__ __forceinline__ bool hot_eval(int op, int xl, int xu, int yl, int yu, int zl, int zu,
+                                         int& nxl, int& nxu, int& nyl, int& nyu, int& nzl, int& nzu) {
+  const bool ground = (xl == xu) & (yl == yu) & (zl == zu);
+  if (op == TB_OP_ADD) {
+    const unsigned B = 0x40000000u;
+    unsigned t = ((unsigned)xl + B) | ((unsigned)xu + B) | ((unsigned)yl + B) | ((unsigned)yu + B) |
+                 ((unsigned)zl + B) | ((unsigned)zu + B);
+    if ((int)t >= 0) {          // all bounds in [-2^30, 2^30): 32-bit arithmetic is exact, no infinity involved
+      nxl = max(xl, yl + zl); nxu = min(xu, yu + zu);
+      nyl = max(yl, xl - zu); nyu = min(yu, xu - zl);
+      nzl = max(zl, xl - yu); nzu = min(zu, xu - yl);
+    } else {
+      Cand c;
+      add(xl, xu, yl, yu, zl, zu, c);
+      nxl = max(xl, c.xl); nxu = min(xu, c.xu); nyl = max(yl, c.yl); nyu = min(yu, c.yu); nzl = max(zl, c.zl); nzu = min(zu, c.zu);
+    }
+    return ground;
+  }
+  if (op == TB_OP_LEQ) {
+    if (xl >= 1) { nyu = min(yu, zu); nzl = max(zl, yl); return yu <= zl; }
+    if (xu <= 0) { nyl = max(yl, succ(zl)); nzu = min(zu, pred(yu)); return yl > zu; }
+    if (yu <= zl) nxl = 1; else if (yl > zu) nxu = 0;
+    return false;
+  }
+  if (op == TB_OP_EQ) {
+    if (xl >= 1) {
+      nyl = max(yl, zl); nyu = min(yu, zu); nzl = nyl; nzu = nyu;
+      return (yl == yu) & (zl == zu) & (yl == zl);
+    }
+    if (xu <= 0) {
+      if (yl == yu && fin(yl, yu)) { if (zl == yl) nzl = yl + 1; if (zu == yl) nzu = yl - 1; }
+      if (zl == zu && fin(zl, zu)) { if (yl == zl) nyl = zl + 1; if (yu == zl) nyu = zl - 1; }
+      return (yu < zl) | (zu < yl);
+    }
+    if (yu < zl || zu < yl) nxu = 0;
+    else if (yl == yu && zl == zu && yl == zl) nxl = 1;
+    return false;
+  }
+  if (op == TB_OP_MIN) {
+    nxl = max(xl, min(yl, zl)); nxu = min(xu, min(yu, zu));
+    nyl = max(yl, xl); nzl = max(zl, xl);
+    if (yl > xu) nzu = min(zu, xu);
+    if (zl > xu) nyu = min(yu, xu);
+    return ground;
+  }
+  if (op == TB_OP_MAX) {
+    nxl = max(xl, max(yl, zl)); nxu = min(xu, max(yu, zu));
+    nyu = min(yu, xu); nzu = min(zu, xu);
+    if (yu < xl) nzl = max(zl, xl);
+    if (zu < xl) nyl = max(yl, xl);
+    return ground;
+  }
+  return true;   // TB_OP_NOP
+}
+
+__device__ __forceinline__ bool is_rare(int op) { return op >= TB_OP_MUL && op <= TB_OP_TMOD; }
 
 }  // namespace tbd
