@@ -94,6 +94,18 @@ class ClockSampler:
         return out
 
 
+def reduce_over_ranks(dist, sums, maxes, device="cpu"):
+    """Whole-job aggregation: counters are summed over ranks, times are the max over ranks."""
+    if dist is None:
+        return [float(x) for x in sums], [float(x) for x in maxes]
+    import torch
+    t = torch.tensor(sums, dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    m = torch.tensor(maxes, dtype=torch.float64, device=device)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()], [float(x) for x in m.tolist()]
+
+
 def problem_bytes(pb):
     return int(pb.lb.nbytes + pb.ub.nbytes + pb.props.nbytes + sum(v.nbytes for _, _, v in pb.strategies))
 
@@ -178,13 +190,8 @@ def run_ours(args):
     d2h = int(2 * 4 * pb.nvars + abi.C.sizeof(abi.TbStats) + 120 * cfg["num_blocks"])
 
     # ---- reduce over ranks: sums of counters, max of times ---------------------------------------------------
-    if dist is not None:
-        t = torch.tensor([ded, nodes, narrowed, e2e_ded], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ded, nodes, narrowed, e2e_ded = (float(x) for x in t.tolist())
-        m = torch.tensor([kernel_ms, e2e_s, wall_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        kernel_ms, e2e_s, wall_s = (float(x) for x in m.tolist())
+    (ded, nodes, narrowed, e2e_ded), (kernel_ms, e2e_s, wall_s) = reduce_over_ranks(
+        dist, [ded, nodes, narrowed, e2e_ded], [kernel_ms, e2e_s, wall_s], device="cuda")
 
     line = None
     if rank == 0:

@@ -33,8 +33,8 @@ typedef enum {
   TB_OP_TMOD = 3,  /* x = y mod z, truncated remainder (int_mod)  */
   TB_OP_MIN  = 4,  /* x = min(y, z)                               */
   TB_OP_MAX  = 5,  /* x = max(y, z)                               */
-  TB_OP_EQ   = 6,  /* x = (y == z), x in 0..1                     */
-  TB_OP_LEQ  = 7,  /* x = (y <= z), x in 0..1                     */
+  TB_OP_EQ   = 6,  /* x = (y == z); precondition: dom(x) within 0..1 (tb_create checks) */
+  TB_OP_LEQ  = 7,  /* x = (y <= z); precondition: dom(x) within 0..1               */
   TB_NUM_OPS = 8
 } tb_op;
 

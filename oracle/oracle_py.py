@@ -41,6 +41,10 @@ def lib():
         L.tbo_solve.argtypes = [C.POINTER(abi.TbProblem), C.c_int32, C.c_uint64, C.c_uint64, C.c_int32,
                                 i32p, i32p, i32p, i32p, i32p, C.POINTER(abi.TbStats)]
         L.tbo_solve.restype = C.c_int
+        L.tbo_solve_shard.argtypes = [C.POINTER(abi.TbProblem), C.c_int32, C.c_uint64, C.c_uint64, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32,
+                                      i32p, i32p, i32p, i32p, i32p, C.POINTER(abi.TbStats)]
+        L.tbo_solve_shard.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -90,15 +94,15 @@ def dive(problem, idx, depth):
     return dict(lb=lb, ub=ub, remaining_depth=rem.value, leaf_kind=kind.value)
 
 
-def solve(problem, depth=0, cutnodes=0, timeout_ms=0, nthreads=1):
+def solve(problem, depth=0, cutnodes=0, timeout_ms=0, nthreads=1, rank=0, world=1, initial_bound=abi.POS_INF):
     n = max(1, problem.nvars)
     lb = np.zeros(n, np.int32)
     ub = np.zeros(n, np.int32)
     has = C.c_int32(0)
     exh = C.c_int32(0)
     st = abi.TbStats()
-    rc = lib().tbo_solve(C.byref(problem.c), depth, cutnodes, timeout_ms, nthreads, None,
-                         _p(lb), _p(ub), C.byref(has), C.byref(exh), C.byref(st))
+    rc = lib().tbo_solve_shard(C.byref(problem.c), depth, cutnodes, timeout_ms, nthreads, rank, world, initial_bound,
+                               None, _p(lb), _p(ub), C.byref(has), C.byref(exh), C.byref(st))
     assert rc == 0, rc
     obj = None
     if has.value and problem.obj_var >= 0:

@@ -276,6 +276,7 @@ typedef struct {
   volatile int32_t* user_stop;
   struct timespec t0;
   uint64_t timeout_ms;
+  uint64_t rank, world;               /* this worker group's shard: idx = k * world + rank */
 } shared_t;
 
 typedef struct {
@@ -511,13 +512,16 @@ static void* block_run(void* arg) {
   block_t* b = (block_t*)arg;
   shared_t* sh = b->sh;
   uint64_t nsub = 1ULL << b->depth_power;
-  uint64_t idx = b->first_idx;
-  while (idx < nsub && !b->stop) {
+  uint64_t k = b->first_idx;
+  for (;;) {
+    uint64_t idx = k * sh->world + sh->rank;
+    if (idx >= nsub || b->stop) break;
     int remaining = dive(b, idx);
     if (b->leaf && !b->stop) {
       uint64_t next = ((idx >> remaining) + 1ULL) << remaining;
+      uint64_t next_k = next <= sh->rank ? 0 : (next - sh->rank + sh->world - 1) / sh->world;
       uint64_t cur = atomic_load(&sh->next_subproblem);
-      while (cur < next && !atomic_compare_exchange_weak(&sh->next_subproblem, &cur, next)) {}
+      while (cur < next_k && !atomic_compare_exchange_weak(&sh->next_subproblem, &cur, next_k)) {}
       if ((idx & ((1ULL << remaining) - 1ULL)) == 0) b->st.eps_skipped_subproblems += next - idx;
     }
     else if (!b->stop) {
@@ -525,7 +529,7 @@ static void* block_run(void* arg) {
       if (!(b->cutnodes && b->st.nodes >= b->cutnodes) && !atomic_load(&sh->stop)) b->st.eps_solved_subproblems++;
     }
     if (b->overflow) { b->st.exhaustive = 0; b->stop = 1; }
-    if (!b->stop) idx = atomic_fetch_add(&sh->next_subproblem, 1);
+    if (!b->stop) k = atomic_fetch_add(&sh->next_subproblem, 1);
   }
   if (!(b->cutnodes && b->st.nodes >= b->cutnodes) && !atomic_load(&sh->stop)) b->st.num_blocks_done = 1;
   b->st.cumulative_time_block_ns = ns_since(&sh->t0);
@@ -536,6 +540,7 @@ int tbo_dive(const tb_problem* pb, uint64_t idx, int32_t depth,
              int32_t* lb_out, int32_t* ub_out, int32_t* remaining_depth, int32_t* leaf_kind) {
   shared_t sh; memset(&sh, 0, sizeof(sh));
   atomic_store(&sh.appx_best_bound, PINF);
+  sh.world = 1;
   clock_gettime(CLOCK_MONOTONIC, &sh.t0);
   block_t b;
   if (!block_init(&b, pb, &sh, depth, 0)) return TB_ERR_NOMEM;
@@ -551,11 +556,22 @@ int tbo_solve(const tb_problem* pb, int32_t depth, uint64_t cutnodes, uint64_t t
               int32_t nthreads, volatile int32_t* stop_flag,
               int32_t* best_lb, int32_t* best_ub, int32_t* has_solution, int32_t* exhaustive,
               tb_stats* stats) {
+  return tbo_solve_shard(pb, depth, cutnodes, timeout_ms, nthreads, 0, 1, TB_POS_INF, stop_flag,
+                         best_lb, best_ub, has_solution, exhaustive, stats);
+}
+
+int tbo_solve_shard(const tb_problem* pb, int32_t depth, uint64_t cutnodes, uint64_t timeout_ms,
+                    int32_t nthreads, int32_t rank, int32_t world, int32_t initial_bound,
+                    volatile int32_t* stop_flag,
+                    int32_t* best_lb, int32_t* best_ub, int32_t* has_solution, int32_t* exhaustive,
+                    tb_stats* stats) {
   if (nthreads < 1) nthreads = 1;
+  if (world < 1 || rank < 0 || rank >= world) return TB_ERR_INVALID;
   if (depth < 0) depth = 0;
   shared_t sh; memset(&sh, 0, sizeof(sh));
-  atomic_store(&sh.appx_best_bound, PINF);
+  atomic_store(&sh.appx_best_bound, initial_bound);
   atomic_store(&sh.next_subproblem, (uint64_t)nthreads);
+  sh.rank = (uint64_t)rank; sh.world = (uint64_t)world;
   sh.user_stop = stop_flag; sh.timeout_ms = timeout_ms;
   clock_gettime(CLOCK_MONOTONIC, &sh.t0);
   block_t* blocks = calloc((size_t)nthreads, sizeof(block_t));

@@ -47,6 +47,15 @@ int tbo_solve(const tb_problem* pb, int32_t depth, uint64_t cutnodes, uint64_t t
               int32_t* best_lb, int32_t* best_ub, int32_t* has_solution, int32_t* exhaustive,
               tb_stats* stats);
 
+/* One GPU's shard of the subproblems (idx = k * world + rank) with an incumbent the
+ * other shards may already have found (initial_bound, TB_POS_INF for none). Used by the world_size-2
+ * gloo tests of the multi-rank host logic. */
+int tbo_solve_shard(const tb_problem* pb, int32_t depth, uint64_t cutnodes, uint64_t timeout_ms,
+                    int32_t nthreads, int32_t rank, int32_t world, int32_t initial_bound,
+                    volatile int32_t* stop_flag,
+                    int32_t* best_lb, int32_t* best_ub, int32_t* has_solution, int32_t* exhaustive,
+                    tb_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,9 +131,11 @@ def test_dive_all_orders(eng, orc, var_order, val_order):
 
 @pytest.mark.parametrize("kind", KINDS)
 def test_solve_status_and_optimum(eng, orc, kind):
-    for seed in range(25):
-        pb = tnf_gen.random_net(16, 18, 3000 + seed, lo=-4, hi=4)
+    nsat = 0
+    for seed in range(30):
+        pb = tnf_gen.search_instance(seed) if seed < 14 else tnf_gen.random_net(16, 9, 5000 + seed, lo=-4, hi=4)
         o = orc.solve(pb, depth=0)
+        nsat += o["has_solution"]
         with eng.Solver(pb, mem_kind=kind, subproblems_power=4) as s:
             g = s.solve()
         assert g["exhaustive"] and o["exhaustive"]
@@ -143,13 +145,14 @@ def test_solve_status_and_optimum(eng, orc, kind):
             from tests.test_oracle_ops import REL
             for p in pb.props:
                 assert REL[int(p["op"])](int(g["lb"][p["x"]]), int(g["lb"][p["y"]]), int(g["lb"][p["z"]]))
+    assert nsat >= 14
 
 
 def test_single_block_node_counts_match_oracle(eng, orc):
     """With one block the subproblems are visited in index order exactly like the oracle, so the
     whole trace (nodes, failures, solutions, skipped/solved subproblems, depth) is comparable."""
-    for seed in range(10):
-        pb = tnf_gen.random_net(18, 20, 4000 + seed, lo=-4, hi=4)
+    for seed in range(12):
+        pb = tnf_gen.search_instance(seed) if seed < 8 else tnf_gen.random_net(18, 10, 4000 + seed, lo=-4, hi=4)
         for depth in (0, 3):
             o = orc.solve(pb, depth=depth)
             with eng.Solver(pb, or_blocks=1, subproblems_power=depth, fixpoint=abi.FP_AC1) as s:

@@ -78,6 +78,11 @@ def planted(nvars, nprops, seed, spread=50, slack=32, mix=None, singleton_frac=0
     ub[isbool] = np.minimum(ub[isbool], 1)
     for k in range(3):
         lb[k] = ub[k] = k
+    # the result of a reified comparison is a 0..1 variable (precondition of TB_OP_EQ / TB_OP_LEQ)
+    for op, x, _, _ in props:
+        if op in (abi.OP_EQ, abi.OP_LEQ):
+            lb[x] = max(lb[x], 0)
+            ub[x] = min(ub[x], 1)
     obj = -1
     if objective:
         obj = int(rng.integers(3, nvars))
@@ -118,3 +123,11 @@ def random_net(nvars, nprops, seed, lo=-6, hi=6, objective=True, mix=None, strat
         props.append((op, x, y, z))
     obj = int(rng.integers(3 + nbool, nvars)) if objective else -1
     return abi.Problem(lb, ub, np.array(props, dtype=np.int32).reshape(-1, 4), strategies, obj_var=obj)
+
+
+def search_instance(seed):
+    """A satisfiable optimisation instance whose proof of optimality needs a real search tree
+    (tens to hundreds of nodes, several improving solutions, backtracking)."""
+    if seed % 2 == 0:
+        return planted(60, 60, 6000 + seed, spread=12, slack=12, objective=True, singleton_frac=0.05)
+    return planted(80, 70, 6000 + seed, spread=10, slack=16, objective=True, singleton_frac=0.05)

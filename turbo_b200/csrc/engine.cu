@@ -846,6 +846,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (p.op < 0 || p.op >= TB_NUM_OPS || p.x < 0 || p.y < 0 || p.z < 0 || p.x >= pb->nvars || p.y >= pb->nvars || p.z >= pb->nvars) {
       set_error("propagator " + std::to_string(i) + " has an invalid operator or variable index"); return TB_ERR_INVALID;
     }
+    if ((p.op == TB_OP_EQ || p.op == TB_OP_LEQ) && (pb->lb[p.x] < 0 || pb->ub[p.x] > 1)) {
+      set_error("propagator " + std::to_string(i) + ": the result variable of EQ/LEQ must have a domain within 0..1"); return TB_ERR_INVALID;
+    }
   }
   if (pb->obj_var >= pb->nvars) { set_error("obj_var out of range"); return TB_ERR_INVALID; }
   for (int i = 0; i < pb->nstrategies; ++i) {

@@ -110,6 +110,9 @@ tb_status tb_model_synthetic(tb_model** out, int32_t nvars, int32_t nprops, uint
     m->ub[v] = s[v] + (int32_t)uni(0, 32);
   }
   for (int k = 0; k < 3; ++k) m->lb[k] = m->ub[k] = k;
+  // the result of a reified comparison is a 0..1 variable (precondition of TB_OP_EQ / TB_OP_LEQ)
+  for (const tb_prop& p : m->props)
+    if (p.op == TB_OP_EQ || p.op == TB_OP_LEQ) { m->lb[p.x] = std::max(m->lb[p.x], 0); m->ub[p.x] = std::min(m->ub[p.x], 1); }
   m->strat_vars.push_back({});
   m->strat_orders.push_back({TB_VAR_FIRST_FAIL, TB_VAL_MIN});
   m->obj_var = -1; m->objective_kind = -1;
