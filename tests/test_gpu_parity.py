@@ -181,3 +181,61 @@ def test_cutnodes_and_stop(eng):
     with eng.Solver(pb, timeout_ms=200) as s:
         g = s.solve()
     assert g["stats"]["timers_ns"][abi.TIMER_OVERALL] < 5e9
+
+
+# ---- STORE_CLUSTER: the store striped over a thread-block cluster's distributed shared memory ---------
+
+@pytest.mark.parametrize("csize", [2, 4, 8])
+@pytest.mark.parametrize("fp", [abi.FP_AC1, abi.FP_WAC1])
+def test_cluster_fixpoint_bit_exact(eng, orc, csize, fp):
+    for seed, (nv, npr) in enumerate([(8, 5), (100, 300), (5000, 20000), (40000, 120000)]):
+        pb = tnf_gen.planted(nv, npr, 70 + seed)
+        o = orc.fixpoint(pb)
+        with eng.Solver(pb, mem_kind=abi.MEM_STORE_CLUSTER, cluster_size=csize, fixpoint=fp) as s:
+            cfg = s.config()
+            assert cfg["mem_kind"] == abi.MEM_STORE_CLUSTER and cfg["cluster_size"] == csize
+            g = s.propagate()
+        assert_same_store(g, o, (csize, fp, nv, npr))
+
+
+def test_cluster_is_chosen_when_the_store_exceeds_one_sm(eng, orc):
+    pb = tnf_gen.planted(60000, 90000, 5)          # 480 KB store: does not fit 227 KB
+    o = orc.fixpoint(pb)
+    with eng.Solver(pb) as s:
+        cfg = s.config()
+        assert cfg["mem_kind"] == abi.MEM_STORE_CLUSTER and cfg["cluster_size"] == 4
+        g = s.propagate()
+    assert_same_store(g, o, "auto cluster")
+
+
+def test_cluster_failed_stores_and_batch(eng, orc):
+    for seed in range(10):
+        pb = tnf_gen.random_net(20, 40, 500 + seed, lo=-5, hi=5)
+        o = orc.fixpoint(pb)
+        with eng.Solver(pb, mem_kind=abi.MEM_STORE_CLUSTER, cluster_size=2) as s:
+            g = s.propagate()
+        assert_same_store(g, o, seed)
+
+
+def test_cluster_dive_and_solve(eng, orc):
+    strat = [(abi.VAR_INPUT_ORDER, abi.VAL_SPLIT, list(range(3, 40))), (abi.VAR_FIRST_FAIL, abi.VAL_MIN, [])]
+    pb = tnf_gen.planted(120, 200, 11, strategies=strat, objective=True)
+    depth = 4
+    with eng.Solver(pb, mem_kind=abi.MEM_STORE_CLUSTER, cluster_size=4) as s:
+        g = s.dive_batch(0, 1 << depth, depth)
+    for idx in range(1 << depth):
+        o = orc.dive(pb, idx, depth)
+        assert g["remaining_depth"][idx] == o["remaining_depth"] and g["leaf_kind"][idx] == o["leaf_kind"], idx
+        if o["leaf_kind"] != 1:
+            assert np.array_equal(g["lb"][idx], o["lb"]) and np.array_equal(g["ub"][idx], o["ub"]), idx
+    for seed in range(8):
+        pb = tnf_gen.search_instance(seed)
+        o = orc.solve(pb, depth=0)
+        with eng.Solver(pb, mem_kind=abi.MEM_STORE_CLUSTER, cluster_size=2, subproblems_power=4) as s:
+            g = s.solve()
+        assert g["exhaustive"] and g["has_solution"] == o["has_solution"] and g["objective"] == o["objective"], seed
+        with eng.Solver(pb, mem_kind=abi.MEM_STORE_CLUSTER, cluster_size=2, or_blocks=1, subproblems_power=3, fixpoint=abi.FP_AC1) as s:
+            g = s.solve()
+        o = orc.solve(pb, depth=3)
+        for key in ("nodes", "fails", "solutions", "eps_solved_subproblems", "eps_skipped_subproblems", "depth_max"):
+            assert g["stats"][key] == o["stats"][key], (seed, key)

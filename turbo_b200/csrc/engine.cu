@@ -112,6 +112,7 @@ struct StoreRef {
   }
   __device__ __forceinline__ int* lbp(int v) const { return AOS ? p + 2 * v : p + v; }
   __device__ __forceinline__ int* ubp(int v) const { return AOS ? p + 2 * v + 1 : p + vpad + v; }
+  __device__ __forceinline__ void set(int v, int l, int u) const { *lbp(v) = l; *ubp(v) = u; }
   __device__ __forceinline__ void tell_lb(int v, int n) const { atomicMax(lbp(v), n); }
   __device__ __forceinline__ void tell_ub(int v, int n) const { atomicMin(ubp(v), n); }
   // VStore::embed (barebones :707,761-764,805,846,853): in-place meet, returns "changed"
@@ -120,6 +121,56 @@ struct StoreRef {
     return l > ol || u < ou;
   }
 };
+
+// Store striped over the distributed shared memory of a thread-block cluster: variable v lives in
+// CTA (v mod C) at local index (v div C); every CTA's slice is lb[vc] | ub[vc] at the same shared
+// offset, reached with mapa + ld/red/atom.shared::cluster.
+template <bool AOS>
+struct StoreRef<TB_MEM_STORE_CLUSTER, AOS> {
+  int* p;          // this CTA's slice (generic pointer)
+  unsigned base;   // its shared::cta address
+  int vpad;        // vc: variables per slice
+  int lc;          // log2(C)
+  unsigned cmask;  // C - 1
+  __device__ __forceinline__ unsigned addr(int v) const {
+    unsigned r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(base + (((unsigned)v >> lc) << 2)), "r"((unsigned)v & cmask));
+    return r;
+  }
+  __device__ __forceinline__ void ld(int v, int& l, int& u) const {
+    const unsigned a = addr(v);
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(l) : "r"(a) : "memory");
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(u) : "r"(a + ((unsigned)vpad << 2)) : "memory");
+  }
+  __device__ __forceinline__ void set(int v, int l, int u) const {
+    const unsigned a = addr(v);
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(l) : "memory");
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a + ((unsigned)vpad << 2)), "r"(u) : "memory");
+  }
+  __device__ __forceinline__ void tell_lb(int v, int n) const {
+    asm volatile("red.shared::cluster.max.s32 [%0], %1;" ::"r"(addr(v)), "r"(n) : "memory");
+  }
+  __device__ __forceinline__ void tell_ub(int v, int n) const {
+    asm volatile("red.shared::cluster.min.s32 [%0], %1;" ::"r"(addr(v) + ((unsigned)vpad << 2)), "r"(n) : "memory");
+  }
+  __device__ __forceinline__ bool embed(int v, int l, int u) const {
+    const unsigned a = addr(v);
+    int ol, ou;
+    asm volatile("atom.shared::cluster.max.s32 %0, [%1], %2;" : "=r"(ol) : "r"(a), "r"(l) : "memory");
+    asm volatile("atom.shared::cluster.min.s32 %0, [%1], %2;" : "=r"(ou) : "r"(a + ((unsigned)vpad << 2)), "r"(u) : "memory");
+    return l > ol || u < ou;
+  }
+};
+
+template <int MEM, bool AOS>
+__device__ __forceinline__ void init_store_ref(StoreRef<MEM, AOS>& st, const DevParams& P, unsigned char* dyn, int slot) {
+  st.vpad = P.vpad;
+  st.p = (MEM == TB_MEM_GLOBAL) ? P.block_store + (size_t)slot * 2 * P.vpad : (int*)dyn;
+}
+template <bool AOS>
+__device__ __forceinline__ void init_store_ref(StoreRef<TB_MEM_STORE_CLUSTER, AOS>& st, const DevParams& P, unsigned char* dyn, int) {
+  st.vpad = P.vc; st.p = (int*)dyn; st.base = smem_u32(dyn); st.lc = P.cluster_log2; st.cmask = (unsigned)P.cluster_size - 1u;
+}
 
 struct RawProp { unsigned long long w; int4 q; };
 
@@ -182,48 +233,66 @@ struct Ctx {
   int* g_best;
   Decision* dec;
   BlockStats* st;
+  Ctl* lc;                 // this CTA's own control block (owns the mbarrier used by its bulk copies)
+  int tid, T;              // thread index / thread count of the worker (a CTA, or a whole cluster)
+  int slot, nslots;        // worker index / number of workers in the grid
+  int cta_rank;            // rank of this CTA inside its cluster (0 without clusters)
 
   __device__ Ctx(const DevParams& P_, Ctl& c_) : P(P_), c(c_) {}
 
+  // Worker-wide barrier: the CTA barrier, or the cluster barrier when the store is striped over DSMEM.
+  __device__ __forceinline__ void sync() const {
+    if (MEM == TB_MEM_STORE_CLUSTER) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else __syncthreads();
+  }
+
   // ---- copies between the block store and a global image of it ---------------------------------
+  // An image is P.vpad * 8 bytes; with a cluster it is C slices of vc * 8 bytes, one per CTA, and every
+  // CTA moves its own slice with its own mbarrier.
   __device__ void load_store(const int* gsrc) {
-    const unsigned bytes = (unsigned)P.vpad * 8u;
+    sync();
     if (MEM == TB_MEM_GLOBAL) {
-      __syncthreads();
+      const unsigned bytes = (unsigned)P.vpad * 8u;
       const int4* s4 = (const int4*)gsrc; int4* d4 = (int4*)store.p;
-      for (unsigned i = threadIdx.x; i < bytes / 16; i += blockDim.x) d4[i] = __ldcg(s4 + i);
-      __syncthreads();
+      for (unsigned i = tid; i < bytes / 16; i += T) d4[i] = __ldcg(s4 + i);
+      sync();
     } else {
-      __syncthreads();
+      const unsigned bytes = (unsigned)store.vpad * 8u;
+      const char* src = (const char*)gsrc + (size_t)cta_rank * bytes;
       if (threadIdx.x == 0) {
         fence_proxy_async();
-        mbar_expect_tx(&c.mbar, bytes);
+        mbar_expect_tx(&lc->mbar, bytes);
         for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-          bulk_g2s_issue((char*)store.p + off, (const char*)gsrc + off, min(BULK_CHUNK, bytes - off), &c.mbar);
+          bulk_g2s_issue((char*)store.p + off, src + off, min(BULK_CHUNK, bytes - off), &lc->mbar);
       }
-      while (!mbar_try_wait(&c.mbar, mbar_phase)) {}
+      while (!mbar_try_wait(&lc->mbar, mbar_phase)) {}
       mbar_phase ^= 1;
+      if (MEM == TB_MEM_STORE_CLUSTER) sync();     // every slice has landed before anybody gathers from it
     }
   }
   __device__ void save_store(int* gdst) {
-    const unsigned bytes = (unsigned)P.vpad * 8u;
-    __syncthreads();
+    sync();
     if (MEM == TB_MEM_GLOBAL) {
+      const unsigned bytes = (unsigned)P.vpad * 8u;
       const int4* s4 = (const int4*)store.p; int4* d4 = (int4*)gdst;
-      for (unsigned i = threadIdx.x; i < bytes / 16; i += blockDim.x) d4[i] = __ldcg(s4 + i);
+      for (unsigned i = tid; i < bytes / 16; i += T) d4[i] = __ldcg(s4 + i);
     } else if (threadIdx.x == 0) {
+      const unsigned bytes = (unsigned)store.vpad * 8u;
+      char* dst = (char*)gdst + (size_t)cta_rank * bytes;
       fence_proxy_async();
       for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-        bulk_s2g_issue((char*)gdst + off, (const char*)store.p + off, min(BULK_CHUNK, bytes - off));
+        bulk_s2g_issue(dst + off, (const char*)store.p + off, min(BULK_CHUNK, bytes - off));
       bulk_commit_wait_all();
     }
-    __syncthreads();
+    sync();
   }
 
   // ---- fixpoint (BlockAsynchronousFixpointGPU::fixpoint + warp_fixpoint, barebones :925-965) ---
   // Returns the OR of the flag bits of the last sweep; `iters` = number of block sweeps.
   __device__ int fixpoint(int& iters) {
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    const int lane = tid & 31;
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
     const int n = P.nprops_pad;
     int it = 0, f;
@@ -267,15 +336,15 @@ struct Ctx {
       const int slot = it % 3;
       if (lane == 0 && bits) atomicOr(&c.flags[slot], bits);
       if (tid == 0) c.flags[(it + 1) % 3] = 0;
-      __syncthreads();
+      sync();
       f = c.flags[slot];
       if (!(f & F_CHANGED) || (f & F_FAILED)) break;
     }
     iters = it + 1;
     // leave slot 0 clean for the next call (nobody reads flags until the next fixpoint's barrier)
-    __syncthreads();
+    sync();
     if (tid < 3) c.flags[tid] = 0;
-    __syncthreads();
+    sync();
     return f;
   }
 
@@ -283,7 +352,7 @@ struct Ctx {
   // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
   // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
   __device__ void propagate() {
-    const int tid = threadIdx.x;
+    
     unsigned long long t0 = 0;
     if (tid == 0) t0 = globaltimer_ns();
     int iters = 0, f;
@@ -300,7 +369,7 @@ struct Ctx {
       if (P.obj_var >= 0) {
         int l, u; store.ld(P.obj_var, l, u);
         improved = c.best_bound > l;           // uniform: same smem word read by everybody
-        __syncthreads();
+        sync();
         if (improved && tid == 0) {
           c.best_bound = l;
           atomicMin(P.appx_best_bound, l);
@@ -310,7 +379,7 @@ struct Ctx {
         }
       } else {
         improved = st->solutions == 0;          // satisfaction: first solution wins
-        __syncthreads();
+        sync();
         if (tid == 0) st->t_best = (long long)(globaltimer_ns() - P.t_start);
       }
       if (improved) {
@@ -338,7 +407,7 @@ struct Ctx {
     }
     if (!(P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold) && tid == 0)
       st->deductions += (unsigned long long)iters * (unsigned long long)P.nprops;
-    __syncthreads();
+    sync();
   }
 
   // ---- branching (BlockData::split / push_decision, barebones :187-405) ----------------------------
@@ -377,7 +446,7 @@ struct Ctx {
 
   // Returns (uniformly) whether a decision was pushed at dec[depth-1].
   __device__ bool split() {
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+    const int lane = tid & 31;
     for (;;) {
       const int s = c.cur_strategy;       // uniform (barrier before every read)
       if (s >= P.nstrategies) return false;
@@ -402,9 +471,9 @@ struct Ctx {
         if (other < key) key = other;
       }
       if (lane == 0 && key != ~0ull) { atomicMin(&c.sel_key, key); atomicMin(&c.sel_first, first); }
-      __syncthreads();
+      sync();
       const unsigned long long best = c.sel_key;
-      __syncthreads();
+      sync();
       if (tid == 0) {
         if (best != ~0ull) {
           c.next_unassigned = c.sel_first;
@@ -416,7 +485,7 @@ struct Ctx {
         }
         c.sel_key = ~0ull; c.sel_first = INT32_MAX;
       }
-      __syncthreads();
+      sync();
       if (best != ~0ull) return c.pushed != 0;
     }
   }
@@ -424,16 +493,16 @@ struct Ctx {
   // ---- EPS dive (barebones :663-741) ------------------------------------------------------------------
   // Dives from the problem root following the bits of `idx`. Returns remaining depth (uniform).
   __device__ int dive(unsigned long long idx, int depth_power) {
-    const int tid = threadIdx.x;
+    
     if (tid == 0) {
       c.cur_strategy = 0; c.next_unassigned = 0; c.depth = 0;
       c.remaining_depth = depth_power; c.leaf = 0; c.failed = 0;
       c.t_mark = (long long)globaltimer_ns();
     }
     load_store(P.root_store);
-    __syncthreads();
+    sync();
     while (c.remaining_depth > 0 && !c.leaf && !c.stop) {
-      __syncthreads();
+      sync();
       propagate();
       if (!c.leaf) {
         bool pushed = split();
@@ -448,18 +517,18 @@ struct Ctx {
           }
         }
       }
-      __syncthreads();
+      sync();
     }
     if (tid == 0) st->t_dive += (long long)globaltimer_ns() - c.t_mark;
-    __syncthreads();
+    sync();
     return c.remaining_depth;
   }
 
   // ---- solve one subproblem (barebones :742-871) -----------------------------------------------------
   __device__ void solve_subproblem() {
-    const int T = blockDim.x, tid = threadIdx.x;
+    
     if (tid == 0 && P.has_eps_strategy) { c.cur_strategy = max(1, c.cur_strategy); c.next_unassigned = 0; }
-    __syncthreads();
+    sync();
     while (!c.stop) {
       // I. inject the incumbent bound (thread 0), detect an unconstrained objective
       if (tid == 0 && P.obj_var >= 0) {
@@ -470,7 +539,7 @@ struct Ctx {
         }
         if (appx == TBD_NINF) { c.stop = 1; *P.stop = 1; }
       }
-      __syncthreads();
+      sync();
       if (c.stop) break;
       // II. propagate
       propagate();
@@ -479,7 +548,7 @@ struct Ctx {
         if (c.depth == 0) {
           save_store(g_root);
           if (tid == 0) { c.snap_strategy = c.cur_strategy; c.snap_next_unassigned = c.next_unassigned; }
-          __syncthreads();
+          sync();
         }
         bool pushed = split();
         if (tid == 0) {
@@ -490,14 +559,14 @@ struct Ctx {
             store.embed(d.var, d.clb0, d.cub0);
           }
         }
-        __syncthreads();
+        sync();
       }
       // IV. backtrack: follow the rope, restore from the subproblem root, replay the decisions
       if (c.leaf) {
         if (c.depth == 0) break;
-        __syncthreads();
+        sync();
         if (tid == 0) { const Decision& d = dec[c.depth - 1]; c.depth = d.cur == 0 ? d.rope0 : d.rope1; }
-        __syncthreads();
+        sync();
         const int depth = c.depth;
         if (depth == -1) break;
         load_store(g_root);
@@ -511,21 +580,43 @@ struct Ctx {
           store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
           c.cur_strategy = c.snap_strategy; c.next_unassigned = c.snap_next_unassigned;
         }
-        __syncthreads();
+        sync();
       }
     }
-    __syncthreads();
+    sync();
   }
 };
 
 // ---- context construction shared by the three kernels -----------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+
+// The control block every CTA of the worker reads: its own, or CTA 0's through DSMEM.
+template <int MEM>
+__device__ __forceinline__ Ctl* shared_ctl(Ctl* local) {
+  if (MEM != TB_MEM_STORE_CLUSTER) return local;
+  unsigned long long g = (unsigned long long)local, r;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"(g), "r"(0u));
+  return (Ctl*)r;
+}
+
 template <int MEM, bool AOS, bool PACKED>
-__device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, unsigned char* dyn, int slot) {
+__device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, Ctl* local, unsigned char* dyn) {
   const DevParams& P = k.P;
-  Ctl& c = k.c;
+  k.lc = local;
+  if (MEM == TB_MEM_STORE_CLUSTER) {
+    const unsigned csize = cluster_nctarank();
+    k.cta_rank = (int)cluster_ctarank();
+    k.tid = k.cta_rank * (int)blockDim.x + (int)threadIdx.x;
+    k.T = (int)(blockDim.x * csize);
+    k.slot = (int)(blockIdx.x / csize);
+    k.nslots = (int)(gridDim.x / csize);
+  } else {
+    k.cta_rank = 0; k.tid = threadIdx.x; k.T = blockDim.x; k.slot = blockIdx.x; k.nslots = gridDim.x;
+  }
+  const int slot = k.slot;
   const size_t store_bytes = (size_t)P.vpad * 8;
-  k.store.vpad = P.vpad;
-  k.store.p = (MEM == TB_MEM_GLOBAL) ? P.block_store + (size_t)slot * 2 * P.vpad : (int*)dyn;
+  init_store_ref(k.store, P, dyn, slot);
   k.props = P.props;
   k.props_in_smem = false;
   k.mbar_phase = 0;
@@ -536,26 +627,26 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, unsigned char
   k.dec = P.decisions + (size_t)slot * P.max_depth;
   k.st = P.stats + slot;
   if (threadIdx.x == 0) {
-    mbar_init(&c.mbar, 1);
-    c.flags[0] = c.flags[1] = c.flags[2] = 0;
-    c.sel_key = ~0ull; c.sel_first = INT32_MAX;
-    c.stop = 0; c.leaf = 0; c.failed = 0; c.depth = 0; c.pushed = 0;
-    c.cur_strategy = 0; c.next_unassigned = 0; c.snap_strategy = 0; c.snap_next_unassigned = 0;
-    c.best_bound = TBD_PINF; c.remaining_depth = 0;
+    mbar_init(&local->mbar, 1);
+    local->flags[0] = local->flags[1] = local->flags[2] = 0;
+    local->sel_key = ~0ull; local->sel_first = INT32_MAX;
+    local->stop = 0; local->leaf = 0; local->failed = 0; local->depth = 0; local->pushed = 0;
+    local->cur_strategy = 0; local->next_unassigned = 0; local->snap_strategy = 0; local->snap_next_unassigned = 0;
+    local->best_bound = TBD_PINF; local->remaining_depth = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  k.sync();
   if (MEM == TB_MEM_TCN_SHARED) {
     // stage the propagator table once: TMA bulk copy global -> shared
     unsigned char* sprops = dyn + store_bytes;
     const unsigned bytes = (unsigned)((size_t)P.nprops_pad * (PACKED ? 8 : 16));
     if (threadIdx.x == 0 && bytes) {
       fence_proxy_async();
-      mbar_expect_tx(&c.mbar, bytes);
+      mbar_expect_tx(&local->mbar, bytes);
       for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-        bulk_g2s_issue(sprops + off, (const char*)P.props + off, min(BULK_CHUNK, bytes - off), &c.mbar);
+        bulk_g2s_issue(sprops + off, (const char*)P.props + off, min(BULK_CHUNK, bytes - off), &local->mbar);
     }
-    if (bytes) { while (!mbar_try_wait(&c.mbar, k.mbar_phase)) {} k.mbar_phase ^= 1; }
+    if (bytes) { while (!mbar_try_wait(&local->mbar, k.mbar_phase)) {} k.mbar_phase ^= 1; }
     k.props = sprops;
     k.props_in_smem = true;
   }
@@ -570,6 +661,7 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, AOS, PACKED>& k) {
     atomicAdd(&k.st->narrowed, (unsigned long long)n);
     if (k.deductions_wac1) atomicAdd(&k.st->deductions, k.deductions_wac1 * 32ull);
   }
+  k.sync();        // with a cluster: nobody leaves while a peer may still touch its shared memory
 }
 
 // ================================================================================================
@@ -580,19 +672,20 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, AOS, PACKED>& k) {
 template <int MEM, bool AOS, bool PACKED>
 __global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ DevParams P) {
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ Ctl c;
+  __shared__ Ctl c_local;
+  Ctl& c = *shared_ctl<MEM>(&c_local);
   Ctx<MEM, AOS, PACKED> k(P, c);
-  ctx_init(k, dyn, blockIdx.x);
-  const int tid = threadIdx.x;
+  ctx_init(k, &c_local, dyn);
+  const int tid = k.tid;
   BlockStats* st = k.st;
-  if (tid == 0) c.subproblem_k = blockIdx.x;
-  __syncthreads();
+  if (tid == 0) c.subproblem_k = (unsigned long long)k.slot;
+  k.sync();
   const unsigned long long nsub = P.num_subproblems;
   const unsigned long long world = (unsigned long long)P.world, rank = (unsigned long long)P.rank;
   for (;;) {
     const unsigned long long idx = c.subproblem_k * world + rank;   // this GPU's shard: idx ≡ rank (mod world)
     if (idx >= nsub || c.stop) break;
-    __syncthreads();
+    k.sync();
     const int remaining = k.dive(idx, P.subproblems_power);
     if (c.leaf && !c.stop) {
       // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
@@ -606,9 +699,9 @@ __global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ Dev
       k.solve_subproblem();
       if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->eps_solved += 1;
     }
-    __syncthreads();
+    k.sync();
     if (tid == 0 && !c.stop) c.subproblem_k = atomicAdd(P.next_subproblem, 1ull);
-    __syncthreads();
+    k.sync();
   }
   if (tid == 0) {
     if (!(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->blocks_done = 1;
@@ -623,20 +716,21 @@ __global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__
                                                          const int* in_lb, const int* in_ub,
                                                          int* out_lb, int* out_ub, int* out_failed, int repeat) {
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ Ctl c;
+  __shared__ Ctl c_local;
+  Ctl& c = *shared_ctl<MEM>(&c_local);
   Ctx<MEM, AOS, PACKED> k(P, c);
-  ctx_init(k, dyn, blockIdx.x);
-  const int tid = threadIdx.x, T = blockDim.x;
-  for (int s = blockIdx.x; s < nstores; s += gridDim.x) {
+  ctx_init(k, &c_local, dyn);
+  const int tid = k.tid, T = k.T;
+  for (int s = k.slot; s < nstores; s += k.nslots) {
     int f = 0, iters = 0;
     for (int r = 0; r < repeat; ++r) {
-      __syncthreads();
+      k.sync();
       for (int v = tid; v < P.vpad; v += T) {
         int l = 0, u = 0;
         if (v < P.nvars) { l = in_lb[(size_t)s * P.nvars + v]; u = in_ub[(size_t)s * P.nvars + v]; }
-        *k.store.lbp(v) = l; *k.store.ubp(v) = u;
+        k.store.set(v, l, u);
       }
-      __syncthreads();
+      k.sync();
       f = k.fixpoint(iters);
       if (tid == 0) {
         k.st->fixpoint_iterations += (unsigned long long)iters;
@@ -645,7 +739,7 @@ __global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__
           k.st->deductions += (unsigned long long)iters * (unsigned long long)P.nprops;
       }
     }
-    __syncthreads();
+    k.sync();
     for (int v = tid; v < P.nvars; v += T) {
       int l, u; k.store.ld(v, l, u);
       out_lb[(size_t)s * P.nvars + v] = l; out_ub[(size_t)s * P.nvars + v] = u;
@@ -660,14 +754,15 @@ template <int MEM, bool AOS, bool PACKED>
 __global__ void __launch_bounds__(1024) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
                                                     int depth, int* out_lb, int* out_ub, int* out_remaining, int* out_kind) {
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ Ctl c;
+  __shared__ Ctl c_local;
+  Ctl& c = *shared_ctl<MEM>(&c_local);
   Ctx<MEM, AOS, PACKED> k(P, c);
-  ctx_init(k, dyn, blockIdx.x);
-  const int tid = threadIdx.x, T = blockDim.x;
-  for (int s = blockIdx.x; s < count; s += gridDim.x) {
-    __syncthreads();
+  ctx_init(k, &c_local, dyn);
+  const int tid = k.tid, T = k.T;
+  for (int s = k.slot; s < count; s += k.nslots) {
+    k.sync();
     int remaining = k.dive(first + (unsigned long long)s, depth);
-    __syncthreads();
+    k.sync();
     for (int v = tid; v < P.nvars; v += T) {
       int l, u; k.store.ld(v, l, u);
       out_lb[(size_t)s * P.nvars + v] = l; out_ub[(size_t)s * P.nvars + v] = u;
@@ -681,6 +776,9 @@ __global__ void __launch_bounds__(1024) dive_kernel(const __grid_constant__ DevP
 // host side
 // ================================================================================================
 
+struct tb_solver;
+static inline size_t img_lb(const tb_solver* s, int v);
+static inline size_t img_ub(const tb_solver* s, int v);
 static thread_local std::string g_last_error;
 static void set_error(const std::string& s) { g_last_error = s; }
 extern "C" const char* tb_last_error(void) { return g_last_error.c_str(); }
@@ -751,11 +849,31 @@ static tb_status dispatch(const tb_solver* s, F&& f) {
     TB_CASE(TB_MEM_GLOBAL)
     TB_CASE(TB_MEM_STORE_SHARED)
     TB_CASE(TB_MEM_TCN_SHARED)
+    case TB_MEM_STORE_CLUSTER:
+      if (s->packed) return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, std::false_type{}, std::true_type{});
+      else return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, std::false_type{}, std::false_type{});
     default: break;
   }
 #undef TB_CASE
   set_error("unsupported memory kind");
   return TB_ERR_UNSUPPORTED;
+}
+
+// Launch `workers` workers: one CTA each, or one cluster of s->cluster CTAs each (STORE_CLUSTER).
+template <class... KArgs, class... Args>
+static cudaError_t launch_workers(const tb_solver* s, void (*kernel)(KArgs...), int workers, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3((unsigned)s->threads);
+  cfg.dynamicSmemBytes = s->shared_bytes;
+  cfg.stream = s->stream;
+  cudaLaunchAttribute attr[1];
+  if (s->mem_kind == TB_MEM_STORE_CLUSTER) {
+    cfg.gridDim = dim3((unsigned)(workers * s->cluster));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)s->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else cfg.gridDim = dim3((unsigned)workers);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -779,14 +897,43 @@ static tb_status configure(tb_solver* s) {
   };
   int kind = s->opt.mem_kind;
   const int b_tcn = blocks_for(store_b + prop_b), b_store = blocks_for(store_b);
+  // cluster tier: smallest power-of-two cluster whose slice (vc * 8 bytes per CTA) fits one SM
+  auto slice_vars = [&](int c) { return ((s->nvars + c - 1) / c + 3) / 4 * 4; };
+  int cluster = 0;
+  for (int c = 2; c <= 16; c *= 2)
+    if (blocks_for((size_t)std::max(4, slice_vars(c)) * 8) >= 1) { cluster = c; break; }
+  if (s->opt.cluster_size > 0) {
+    cluster = s->opt.cluster_size;
+    if ((cluster & (cluster - 1)) != 0 || cluster > 16 || blocks_for((size_t)std::max(4, slice_vars(cluster)) * 8) < 1) {
+      set_error("cluster_size must be a power of two <= 16 whose slice fits in shared memory"); return TB_ERR_INVALID;
+    }
+  }
   if (kind == TB_MEM_AUTO) {
     // Prefer the propagator table in shared memory unless that costs most of the resident blocks.
     if (b_tcn >= 1 && (b_tcn >= 4 || b_tcn * 2 >= std::min(b_store, 8))) kind = TB_MEM_TCN_SHARED;
     else if (b_store >= 1) kind = TB_MEM_STORE_SHARED;
-    else kind = TB_MEM_GLOBAL;    // STORE_CLUSTER is chosen by the cluster engine (cluster.cu) before we get here
+    else if (cluster >= 2) kind = TB_MEM_STORE_CLUSTER;    // the store is larger than one SM: stripe it over DSMEM
+    else kind = TB_MEM_GLOBAL;
   }
   if (kind == TB_MEM_TCN_SHARED && b_tcn < 1) { set_error("TCN_SHARED does not fit in shared memory"); return TB_ERR_INVALID; }
   if (kind == TB_MEM_STORE_SHARED && b_store < 1) { set_error("STORE_SHARED does not fit in shared memory"); return TB_ERR_INVALID; }
+  if (kind == TB_MEM_STORE_CLUSTER) {
+    if (cluster < 2) { set_error("STORE_CLUSTER: no cluster size up to 16 holds this store"); return TB_ERR_INVALID; }
+    s->cluster = cluster;
+    s->P.cluster_size = cluster;
+    s->P.cluster_log2 = 0;
+    while ((1 << s->P.cluster_log2) < cluster) ++s->P.cluster_log2;
+    s->P.vc = std::max(4, slice_vars(cluster));
+    s->P.vpad = s->P.vc * cluster;               // an image is `cluster` slices of vc variables
+    s->store_bytes = (size_t)s->P.vpad * 8;
+    s->mem_kind = kind;
+    s->shared_bytes = (size_t)s->P.vc * 8;
+    s->threads = s->opt.threads_per_block > 0 ? std::max(32, std::min(1024, (s->opt.threads_per_block + 31) / 32 * 32)) : 1024;
+    s->blocks_per_sm = 1;
+    // how many clusters can be co-resident is asked from the driver once the kernel attributes are set
+    s->num_blocks = std::max(1, s->num_sms / cluster);
+    return TB_OK;
+  }
   s->mem_kind = kind;
   s->shared_bytes = kind == TB_MEM_TCN_SHARED ? store_b + prop_b : (kind == TB_MEM_STORE_SHARED ? store_b : 0);
   int bps = kind == TB_MEM_TCN_SHARED ? b_tcn : (kind == TB_MEM_STORE_SHARED ? b_store : 8);
@@ -816,6 +963,27 @@ static tb_status set_smem_attr(tb_solver* s) {
       CU(cudaFuncSetAttribute(solve_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
       CU(cudaFuncSetAttribute(propagate_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
       CU(cudaFuncSetAttribute(dive_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+    }
+    if (m == TB_MEM_STORE_CLUSTER) {
+      if (s->cluster > 8) {
+        CU(cudaFuncSetAttribute(solve_kernel<m, a, k>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(propagate_kernel<m, a, k>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(dive_kernel<m, a, k>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.blockDim = dim3((unsigned)s->threads);
+      cfg.gridDim = dim3((unsigned)(s->cluster * s->num_sms));
+      cfg.dynamicSmemBytes = s->shared_bytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)s->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int nclusters = 0;
+      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m, a, k>, &cfg));
+      if (nclusters < 1) { set_error("the device cannot host a cluster of this size"); return TB_ERR_UNSUPPORTED; }
+      int workers = nclusters;
+      if (s->opt.or_blocks > 0) workers = std::min(workers, s->opt.or_blocks);
+      s->num_blocks = std::max(1, workers);
     }
     return TB_OK;
   });
@@ -865,7 +1033,6 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   if (opt.gpu_world <= 0) { opt.gpu_world = 1; opt.gpu_rank = 0; }
   if (opt.gpu_rank < 0 || opt.gpu_rank >= opt.gpu_world) { set_error("gpu_rank out of range"); return TB_ERR_INVALID; }
   if (opt.subproblems_factor <= 0) opt.subproblems_factor = 300;
-  if (opt.mem_kind == TB_MEM_STORE_CLUSTER) { set_error("STORE_CLUSTER is served by the cluster engine"); return TB_ERR_UNSUPPORTED; }
 
   tb_solver* s = new tb_solver();
   s->opt = opt;
@@ -896,10 +1063,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   // ---- device images ---------------------------------------------------------------------------------
   {
     std::vector<int> img((size_t)2 * P.vpad, 0);
-    for (int v = 0; v < pb->nvars; ++v) {
-      if (s->aos) { img[2 * v] = pb->lb[v]; img[2 * v + 1] = pb->ub[v]; }
-      else { img[v] = pb->lb[v]; img[P.vpad + v] = pb->ub[v]; }
-    }
+    for (int v = 0; v < pb->nvars; ++v) { img[img_lb(s, v)] = pb->lb[v]; img[img_ub(s, v)] = pb->ub[v]; }
     int* d = nullptr;
     if ((rc = dev_alloc(s, &d, img.size()))) return fail(rc);
     if (cudaMemcpy(d, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D root store"); return fail(TB_ERR_CUDA); }
@@ -1042,12 +1206,17 @@ static void reduce_stats(const std::vector<BlockStats>& bs, tb_stats* st, int* b
   if (best_block) *best_block = best;
 }
 
+// Position of lb[v] / ub[v] inside a store image (SoA, AoS pairs, or cluster slices lb[vc]|ub[vc] per CTA).
+static inline size_t img_lb(const tb_solver* s, int v) {
+  if (s->mem_kind == TB_MEM_STORE_CLUSTER) { const int c = s->cluster, vc = s->P.vc; return (size_t)(v % c) * 2 * vc + (size_t)(v / c); }
+  return s->aos ? (size_t)2 * v : (size_t)v;
+}
+static inline size_t img_ub(const tb_solver* s, int v) {
+  if (s->mem_kind == TB_MEM_STORE_CLUSTER) { const int c = s->cluster, vc = s->P.vc; return (size_t)(v % c) * 2 * vc + vc + (size_t)(v / c); }
+  return s->aos ? (size_t)2 * v + 1 : (size_t)s->P.vpad + v;
+}
 static void unpack_store(const tb_solver* s, const int* img, int32_t* lb, int32_t* ub) {
-  const int vp = s->P.vpad;
-  for (int v = 0; v < s->nvars; ++v) {
-    if (s->aos) { lb[v] = img[2 * v]; ub[v] = img[2 * v + 1]; }
-    else { lb[v] = img[v]; ub[v] = img[vp + v]; }
-  }
+  for (int v = 0; v < s->nvars; ++v) { lb[v] = img[img_lb(s, v)]; ub[v] = img[img_ub(s, v)]; }
 }
 
 static unsigned long long host_globaltimer_probe(tb_solver* s);
@@ -1085,8 +1254,7 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   CU(cudaMemcpyAsync(s->d_next, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
   rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    solve_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>
-        <<<s->num_blocks, s->threads, s->shared_bytes, s->stream>>>(P);
+    CU(launch_workers(s, solve_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>, s->num_blocks, P));
     CU(cudaGetLastError());
     return TB_OK;
   });
@@ -1174,8 +1342,8 @@ extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int
   const int repeat = std::max(1, s->opt.propagate_repeat);
   CU(cudaEventRecord(s->ev_start, s->stream));
   rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    propagate_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>
-        <<<grid, s->threads, s->shared_bytes, s->stream>>>(s->P, nstores, s->d_in_lb, s->d_in_ub, s->d_out_lb, s->d_out_ub, s->d_out_i0, repeat);
+    CU(launch_workers(s, propagate_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>, grid, s->P, nstores,
+                      (const int*)s->d_in_lb, (const int*)s->d_in_ub, s->d_out_lb, s->d_out_ub, s->d_out_i0, repeat));
     CU(cudaGetLastError());
     return TB_OK;
   });
@@ -1221,8 +1389,8 @@ extern "C" tb_status tb_dive_batch(tb_solver* s, uint64_t first, int32_t count, 
   P.cutnodes = 0;
   P.t_start = 0;
   rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    dive_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>
-        <<<grid, s->threads, s->shared_bytes, s->stream>>>(P, first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1);
+    CU(launch_workers(s, dive_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>, grid, P,
+                      (unsigned long long)first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1));
     CU(cudaGetLastError());
     return TB_OK;
   });

@@ -34,6 +34,7 @@ struct DevParams {
   const DevStrategy* strategies;
   unsigned long long num_subproblems, cutnodes, t_start;
   int rank, world, max_depth, npeers;
+  int cluster_size, cluster_log2, vc, pad0_;   // STORE_CLUSTER: CTAs per cluster, its log2, variables per CTA slice
   // per-block scratch in global memory, [slot] major
   int* block_root;              // snapshot of the subproblem root (root_store, barebones :89)
   int* block_best;              // best solution of the block (best_store, :92)
