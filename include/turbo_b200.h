@@ -164,6 +164,20 @@ tb_status tb_read_bound(tb_solver*, int32_t* bound);
 /* Fills `stats` with the launch configuration chosen by tb_create (num_blocks, mem_kind, ...). */
 tb_status tb_get_config(tb_solver*, tb_stats* stats);
 
+/* Introspection of the host layout pass that compiles the propagator table for the device (no GPU
+ * needed): how many propagators fall in each device class (operator x constant operands x exact 32-bit
+ * arithmetic), how the variables are placed over the shared-memory banks, and the bank model's average
+ * number of wavefronts per half-warp load of an 8-byte {lb, ub} pair (1.0 = conflict free).
+ * nbanks = 0 keeps the caller's numbering, 16 = bank-aware placement (16 8-byte banks). slot_of may be NULL. */
+typedef struct {
+  int32_t nclasses, nchunks, nslots, identity;
+  int32_t class_count[32];
+  uint64_t loads_per_sweep;        /* 8-byte {lb, ub} loads one sweep over the table issues */
+  double wavefronts_per_load;
+} tb_layout_info;
+tb_status tb_layout_describe(const tb_problem* problem, int32_t nbanks, tb_layout_info* info, int32_t* slot_of);
+const char* tb_layout_class_name(int32_t cls);
+
 void tb_destroy(tb_solver*);
 const char* tb_last_error(void);
 const char* tb_version(void);

@@ -81,6 +81,11 @@ class TbStats(C.Structure):
         return d
 
 
+class TbLayoutInfo(C.Structure):
+    _fields_ = [("nclasses", C.c_int32), ("nchunks", C.c_int32), ("nslots", C.c_int32), ("identity", C.c_int32),
+                ("class_count", C.c_int32 * 32), ("loads_per_sweep", C.c_uint64), ("wavefronts_per_load", C.c_double)]
+
+
 def default_options(**kw):
     o = TbOptions()
     o.fixpoint = FP_WAC1

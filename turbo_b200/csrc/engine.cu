@@ -29,6 +29,7 @@
 #include "../../include/turbo_b200.h"
 #include "engine_internal.h"
 #include "tnf_device.cuh"
+#include "layout.h"
 
 // ================================================================================================
 // device helpers
@@ -97,138 +98,124 @@ struct Ctl {                       // per-CTA control block in static shared mem
   long long t_mark;
 };
 
-template <int MEM, bool AOS>
-struct StoreRef {
-  int* p;      // shared (MEM != GLOBAL) or global
-  int vpad;
-  __device__ __forceinline__ void ld(int v, int& l, int& u) const {
-    if (AOS) {
-      int2 t = (MEM == TB_MEM_GLOBAL) ? __ldcg((const int2*)(p + 2 * v)) : *(const int2*)(p + 2 * v);
-      l = t.x; u = t.y;
-    } else {
-      l = (MEM == TB_MEM_GLOBAL) ? __ldcg(p + v) : p[v];
-      u = (MEM == TB_MEM_GLOBAL) ? __ldcg(p + vpad + v) : p[vpad + v];
-    }
+// The block store: one {lb, ub} pair of int32 per slot.  All accesses are volatile inline PTX on explicit
+// addresses: the fixpoint loop re-reads bounds other warps narrow concurrently, so a load must never be
+// cached in a register across iterations, and the 32-bit shared address of a slot is one LEA.
+template <int MEM>
+struct StoreRef {           // STORE_SHARED / TCN_SHARED: shared memory of this CTA
+  unsigned base;            // shared::cta address of slot 0
+  __device__ __forceinline__ unsigned addr(int v) const {
+    unsigned r;            // one IMAD; opaque so that the mask of the field decode is not re-associated around it
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(r) : "r"((unsigned)v), "r"(base));
+    return r;
   }
-  __device__ __forceinline__ int* lbp(int v) const { return AOS ? p + 2 * v : p + v; }
-  __device__ __forceinline__ int* ubp(int v) const { return AOS ? p + 2 * v + 1 : p + vpad + v; }
-  __device__ __forceinline__ void set(int v, int l, int u) const { *lbp(v) = l; *ubp(v) = u; }
-  __device__ __forceinline__ void tell_lb(int v, int n) const { atomicMax(lbp(v), n); }
-  __device__ __forceinline__ void tell_ub(int v, int n) const { atomicMin(ubp(v), n); }
+  __device__ __forceinline__ void ld(int v, int& l, int& u) const {
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(u) : "r"(addr(v)));
+  }
+  __device__ __forceinline__ void set(int v, int l, int u) const {
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr(v)), "r"(l), "r"(u) : "memory");
+  }
+  __device__ __forceinline__ void tell_lb(int v, int n) const {
+    asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr(v)), "r"(n) : "memory");
+  }
+  __device__ __forceinline__ void tell_ub(int v, int n) const {
+    asm volatile("red.shared.min.s32 [%0+4], %1;" ::"r"(addr(v)), "r"(n) : "memory");
+  }
   // VStore::embed (barebones :707,761-764,805,846,853): in-place meet, returns "changed"
   __device__ __forceinline__ bool embed(int v, int l, int u) const {
-    int ol = atomicMax(lbp(v), l), ou = atomicMin(ubp(v), u);
+    int ol, ou;
+    asm volatile("atom.shared.max.s32 %0, [%1], %2;" : "=r"(ol) : "r"(addr(v)), "r"(l) : "memory");
+    asm volatile("atom.shared.min.s32 %0, [%1+4], %2;" : "=r"(ou) : "r"(addr(v)), "r"(u) : "memory");
     return l > ol || u < ou;
   }
 };
 
-// Store striped over the distributed shared memory of a thread-block cluster: variable v lives in
-// CTA (v mod C) at local index (v div C); every CTA's slice is lb[vc] | ub[vc] at the same shared
+template <>
+struct StoreRef<TB_MEM_GLOBAL> {   // L2-resident global memory (ld.cg: never through the non-coherent L1)
+  int2* p;
+  __device__ __forceinline__ void ld(int v, int& l, int& u) const {
+    asm volatile("ld.global.cg.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(u) : "l"(p + v));
+  }
+  __device__ __forceinline__ void set(int v, int l, int u) const {
+    asm volatile("st.global.cg.v2.s32 [%0], {%1, %2};" ::"l"(p + v), "r"(l), "r"(u) : "memory");
+  }
+  __device__ __forceinline__ void tell_lb(int v, int n) const { atomicMax(&p[v].x, n); }
+  __device__ __forceinline__ void tell_ub(int v, int n) const { atomicMin(&p[v].y, n); }
+  __device__ __forceinline__ bool embed(int v, int l, int u) const {
+    int ol = atomicMax(&p[v].x, l), ou = atomicMin(&p[v].y, u);
+    return l > ol || u < ou;
+  }
+};
+
+// Store striped over the distributed shared memory of a thread-block cluster: slot v lives in
+// CTA (v mod C) at local index (v div C); every CTA's slice is vc {lb, ub} pairs at the same shared
 // offset, reached with mapa + ld/red/atom.shared::cluster.
-template <bool AOS>
-struct StoreRef<TB_MEM_STORE_CLUSTER, AOS> {
-  int* p;          // this CTA's slice (generic pointer)
-  unsigned base;   // its shared::cta address
-  int vpad;        // vc: variables per slice
+template <>
+struct StoreRef<TB_MEM_STORE_CLUSTER> {
+  unsigned base;   // shared::cta address of this CTA's slice
   int lc;          // log2(C)
   unsigned cmask;  // C - 1
   __device__ __forceinline__ unsigned addr(int v) const {
     unsigned r;
-    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(base + (((unsigned)v >> lc) << 2)), "r"((unsigned)v & cmask));
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(base + (((unsigned)v >> lc) << 3)), "r"((unsigned)v & cmask));
     return r;
   }
   __device__ __forceinline__ void ld(int v, int& l, int& u) const {
-    const unsigned a = addr(v);
-    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(l) : "r"(a) : "memory");
-    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(u) : "r"(a + ((unsigned)vpad << 2)) : "memory");
+    asm volatile("ld.shared::cluster.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(u) : "r"(addr(v)));
   }
   __device__ __forceinline__ void set(int v, int l, int u) const {
-    const unsigned a = addr(v);
-    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(l) : "memory");
-    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a + ((unsigned)vpad << 2)), "r"(u) : "memory");
+    asm volatile("st.shared::cluster.v2.s32 [%0], {%1, %2};" ::"r"(addr(v)), "r"(l), "r"(u) : "memory");
   }
   __device__ __forceinline__ void tell_lb(int v, int n) const {
     asm volatile("red.shared::cluster.max.s32 [%0], %1;" ::"r"(addr(v)), "r"(n) : "memory");
   }
   __device__ __forceinline__ void tell_ub(int v, int n) const {
-    asm volatile("red.shared::cluster.min.s32 [%0], %1;" ::"r"(addr(v) + ((unsigned)vpad << 2)), "r"(n) : "memory");
+    asm volatile("red.shared::cluster.min.s32 [%0], %1;" ::"r"(addr(v) + 4u), "r"(n) : "memory");
   }
   __device__ __forceinline__ bool embed(int v, int l, int u) const {
     const unsigned a = addr(v);
     int ol, ou;
     asm volatile("atom.shared::cluster.max.s32 %0, [%1], %2;" : "=r"(ol) : "r"(a), "r"(l) : "memory");
-    asm volatile("atom.shared::cluster.min.s32 %0, [%1], %2;" : "=r"(ou) : "r"(a + ((unsigned)vpad << 2)), "r"(u) : "memory");
+    asm volatile("atom.shared::cluster.min.s32 %0, [%1], %2;" : "=r"(ou) : "r"(a + 4u), "r"(u) : "memory");
     return l > ol || u < ou;
   }
 };
 
-template <int MEM, bool AOS>
-__device__ __forceinline__ void init_store_ref(StoreRef<MEM, AOS>& st, const DevParams& P, unsigned char* dyn, int slot) {
-  st.vpad = P.vpad;
-  st.p = (MEM == TB_MEM_GLOBAL) ? P.block_store + (size_t)slot * 2 * P.vpad : (int*)dyn;
+template <int MEM>
+__device__ __forceinline__ void init_store_ref(StoreRef<MEM>& st, const DevParams&, unsigned char* dyn, int) {
+  // volatile: keep the base in a register instead of re-deriving it (4 instructions) at every chunk
+  asm volatile("mov.u32 %0, %1;" : "=r"(st.base) : "r"(smem_u32(dyn)));
 }
-template <bool AOS>
-__device__ __forceinline__ void init_store_ref(StoreRef<TB_MEM_STORE_CLUSTER, AOS>& st, const DevParams& P, unsigned char* dyn, int) {
-  st.vpad = P.vc; st.p = (int*)dyn; st.base = smem_u32(dyn); st.lc = P.cluster_log2; st.cmask = (unsigned)P.cluster_size - 1u;
+template <>
+__device__ __forceinline__ void init_store_ref<TB_MEM_GLOBAL>(StoreRef<TB_MEM_GLOBAL>& st, const DevParams& P, unsigned char*, int slot) {
+  st.p = (int2*)(P.block_store + (size_t)slot * 2 * P.vpad);
 }
-
-struct RawProp { unsigned long long w; int4 q; };
-
-template <bool PACKED>
-__device__ __forceinline__ RawProp load_raw(const void* props, int i, bool in_smem) {
-  RawProp r;
-  if (PACKED) r.w = in_smem ? ((const unsigned long long*)props)[i] : __ldg((const unsigned long long*)props + i);
-  else r.q = in_smem ? ((const int4*)props)[i] : __ldg((const int4*)props + i);
-  return r;
-}
-template <bool PACKED>
-__device__ __forceinline__ void decode_raw(const RawProp& r, int& op, int& x, int& y, int& z) {
-  if (PACKED) {
-    const unsigned hi = (unsigned)(r.w >> 32), lo = (unsigned)r.w;
-    op = (int)(hi >> 28); x = (int)((hi >> 8) & 0xFFFFFu); y = (int)(((hi & 0xFFu) << 12) | (lo >> 20)); z = (int)(lo & 0xFFFFFu);
-  } else { op = r.q.x; x = r.q.y; y = r.q.z; z = r.q.w; }
+template <>
+__device__ __forceinline__ void init_store_ref<TB_MEM_STORE_CLUSTER>(StoreRef<TB_MEM_STORE_CLUSTER>& st, const DevParams& P, unsigned char* dyn, int) {
+  st.base = smem_u32(dyn); st.lc = P.cluster_log2; st.cmask = (unsigned)P.cluster_size - 1u;
 }
 
-// One evaluation of one propagator: 6 loads, new bounds in registers, publish only what narrowed.
-// In the steady state nothing narrows, so the common path is loads + arithmetic + one predicate.
-template <class Store>
-__device__ __forceinline__ int deduce(const Store& s, int op, int x, int y, int z, unsigned& narrowed) {
-  int xl, xu, yl, yu, zl, zu;
-  s.ld(x, xl, xu); s.ld(y, yl, yu); s.ld(z, zl, zu);
-  if ((xl > xu) | (yl > yu) | (zl > zu)) return F_FAILED | F_NOT_ENTAILED;
-  int nxl = xl, nxu = xu, nyl = yl, nyu = yu, nzl = zl, nzu = zu;
-  bool entailed;
-  if (!tbd::is_rare(op)) entailed = tbd::hot_eval(op, xl, xu, yl, yu, zl, zu, nxl, nxu, nyl, nyu, nzl, nzu);
-  else {
-    tbd::Cand c;
-    tbd::rare_eval(op, xl, xu, yl, yu, zl, zu, &c);
-    nxl = max(xl, c.xl); nxu = min(xu, c.xu); nyl = max(yl, c.yl); nyu = min(yu, c.yu); nzl = max(zl, c.zl); nzu = min(zu, c.zu);
-    entailed = (xl == xu) & (yl == yu) & (zl == zu);
-  }
-  int bits = entailed ? 0 : F_NOT_ENTAILED;
-  if ((nxl != xl) | (nxu != xu) | (nyl != yl) | (nyu != yu) | (nzl != zl) | (nzu != zu)) {
-    bits |= F_CHANGED;
-    if (nxl != xl) { s.tell_lb(x, nxl); ++narrowed; }
-    if (nxu != xu) { s.tell_ub(x, nxu); ++narrowed; }
-    if (nyl != yl) { s.tell_lb(y, nyl); ++narrowed; }
-    if (nyu != yu) { s.tell_ub(y, nyu); ++narrowed; }
-    if (nzl != zl) { s.tell_lb(z, nzl); ++narrowed; }
-    if (nzu != zu) { s.tell_ub(z, nzu); ++narrowed; }
-    if ((nxl > nxu) | (nyl > nyu) | (nzl > nzu)) bits |= F_FAILED;
-  }
-  return bits;
+// The three 21-bit fields of a device propagator word (tnf_classes.h); constants are sign-extended.
+template <int CLS>
+__device__ __forceinline__ void decode_word(unsigned long long w, int& a, int& b, int& c) {
+  const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+  a = (int)(lo & TBC_FIELD_MASK);
+  b = (int)(__funnelshift_r(lo, hi, TBC_FIELD_BITS) & TBC_FIELD_MASK);
+  c = (int)(hi >> (2 * TBC_FIELD_BITS - 32));          // bit 63 of a word is zero
+  if (CLS == TBC_ADD_XK) a = (a << (32 - TBC_FIELD_BITS)) >> (32 - TBC_FIELD_BITS);
+  if (!tbd::cls_loads_z(CLS)) c = (c << (32 - TBC_FIELD_BITS)) >> (32 - TBC_FIELD_BITS);
 }
 
-template <int MEM, bool AOS, bool PACKED>
+template <int MEM>
 struct Ctx {
   const DevParams& P;
   Ctl& c;
-  StoreRef<MEM, AOS> store;
-  const void* props;       // global or shared
-  bool props_in_smem;
+  StoreRef<MEM> store;
+  unsigned char* sdyn;     // dynamic shared memory: the store image of this CTA (shared placements)
+  const unsigned long long* words;   // the propagator table: global (L2) or shared (TCN_SHARED)
   unsigned mbar_phase;
   unsigned narrowed;       // per-thread count of published bounds
-  unsigned long long deductions_wac1;  // per-warp (lane-uniform) inner iterations
+  unsigned long long deductions;     // per-warp (lane-uniform) count of propagator evaluations
   int* g_root;             // this block's snapshot (global, same layout as the store)
   int* g_best;
   Decision* dec;
@@ -255,17 +242,17 @@ struct Ctx {
     sync();
     if (MEM == TB_MEM_GLOBAL) {
       const unsigned bytes = (unsigned)P.vpad * 8u;
-      const int4* s4 = (const int4*)gsrc; int4* d4 = (int4*)store.p;
+      const int4* s4 = (const int4*)gsrc; int4* d4 = (int4*)(MEM == TB_MEM_GLOBAL ? (void*)P.block_store + (size_t)slot * 8 * P.vpad : (void*)sdyn);
       for (unsigned i = tid; i < bytes / 16; i += T) d4[i] = __ldcg(s4 + i);
       sync();
     } else {
-      const unsigned bytes = (unsigned)store.vpad * 8u;
+      const unsigned bytes = (unsigned)(MEM == TB_MEM_STORE_CLUSTER ? P.vc : P.vpad) * 8u;
       const char* src = (const char*)gsrc + (size_t)cta_rank * bytes;
       if (threadIdx.x == 0) {
         fence_proxy_async();
         mbar_expect_tx(&lc->mbar, bytes);
         for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-          bulk_g2s_issue((char*)store.p + off, src + off, min(BULK_CHUNK, bytes - off), &lc->mbar);
+          bulk_g2s_issue((char*)sdyn + off, src + off, min(BULK_CHUNK, bytes - off), &lc->mbar);
       }
       while (!mbar_try_wait(&lc->mbar, mbar_phase)) {}
       mbar_phase ^= 1;
@@ -276,62 +263,96 @@ struct Ctx {
     sync();
     if (MEM == TB_MEM_GLOBAL) {
       const unsigned bytes = (unsigned)P.vpad * 8u;
-      const int4* s4 = (const int4*)store.p; int4* d4 = (int4*)gdst;
+      const int4* s4 = (const int4*)(MEM == TB_MEM_GLOBAL ? (const void*)P.block_store + (size_t)slot * 8 * P.vpad : (const void*)sdyn); int4* d4 = (int4*)gdst;
       for (unsigned i = tid; i < bytes / 16; i += T) d4[i] = __ldcg(s4 + i);
     } else if (threadIdx.x == 0) {
-      const unsigned bytes = (unsigned)store.vpad * 8u;
+      const unsigned bytes = (unsigned)(MEM == TB_MEM_STORE_CLUSTER ? P.vc : P.vpad) * 8u;
       char* dst = (char*)gdst + (size_t)cta_rank * bytes;
       fence_proxy_async();
       for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-        bulk_s2g_issue(dst + off, (const char*)store.p + off, min(BULK_CHUNK, bytes - off));
+        bulk_s2g_issue(dst + off, (const char*)sdyn + off, min(BULK_CHUNK, bytes - off));
       bulk_commit_wait_all();
     }
     sync();
   }
 
   // ---- fixpoint (BlockAsynchronousFixpointGPU::fixpoint + warp_fixpoint, barebones :925-965) ---
+  // The part of one sweep that falls in class CLS. A warp walks the whole table ch = warp, warp + nwarps, ...
+  // (so the classes load-balance together and the next chunk's words are always prefetched, across class
+  // boundaries too); the table is sorted by class, so the walk is a chain of per-class loops in each of which
+  // the operator is a compile-time constant. A chunk is 32 propagators of one class. With WAC1
+  // (`warp_fixpoint`, :951-962) the warp iterates the chunk to a warp-local fixpoint before moving on.
+  // `changed` / `failed` are warp-uniform; `notent` is per lane: the fused `ask` (:972-982) evaluated on the
+  // last snapshot, which in the sweep where nothing changed is the final store.
+  struct Walk {
+    int ch;                 // current chunk of this warp
+    int widx;               // index of this lane's word in the warp's NEXT chunk
+    unsigned long long cur; // this lane's word of the current chunk
+    unsigned evals;         // warp evaluations (x32 propagators) of this sweep
+    unsigned late_chg;      // chunk visits that ended on a change (AC1: every changing visit)
+    unsigned pad_evals;     // propagator evaluations spent on padding lanes
+    int failed;             // warp-uniform
+    int notent;             // per lane: some propagator of this lane is not entailed
+  };
+
+  // Next chunk's word. The global table is followed by 32 chunks of padding, so the prefetch needs no bound
+  // check; the shared copy (TCN_SHARED) is not, and clamps.
+  __device__ __forceinline__ unsigned long long load_word(int i) const {
+    if (MEM == TB_MEM_TCN_SHARED) return words[min(i, P.nchunks * 32 - 1)];
+    return __ldg(words + i);
+  }
+
+  template <int CLS>
+  __device__ __forceinline__ void sweep_class(Walk& w, const bool wac1, const int nwarps) {
+    const int ce = P.cls_begin[CLS + 1];
+    if (w.ch >= ce) return;
+    unsigned e0;
+    do {
+      const unsigned long long nxt = load_word(w.widx);
+      int fa, fb, fc;
+      decode_word<CLS>(w.cur, fa, fb, fc);
+      tbd::Snap s;
+      e0 = w.evals;
+      bool wchg, wfail;
+      do {
+        bool chg, fail;
+        tbd::deduce<CLS>(store, fa, fb, fc, s, narrowed, chg, fail);
+        wchg = __any_sync(0xffffffffu, chg); wfail = __any_sync(0xffffffffu, fail);
+        ++w.evals;
+      } while (wac1 & wchg & !wfail);
+      if (wchg) ++w.late_chg;
+      if (!tbd::entailed<CLS>(s)) w.notent = 1;
+      if (wfail | __any_sync(0xffffffffu, tbd::snapshot_empty<CLS>(s))) { w.failed = 1; return; }
+      w.ch += nwarps;
+      w.widx += nwarps * 32;
+      w.cur = nxt;
+    } while (w.ch < ce);
+    // the class's last chunk is padded with copies of its last propagator: do not count those lanes
+    if (w.ch - nwarps == ce - 1) w.pad_evals += (w.evals - e0) * (unsigned)(32 - P.cls_last[CLS]);
+  }
+
   // Returns the OR of the flag bits of the last sweep; `iters` = number of block sweeps.
   __device__ int fixpoint(int& iters) {
-    const int lane = tid & 31;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
-    const int n = P.nprops_pad;
     int it = 0, f;
     for (;; ++it) {
-      int bits = 0;
-      if (wac1) {
-        // each warp owns chunks of 32 consecutive propagators; the next chunk's words are prefetched
-        // while the current chunk iterates to its warp-local fixpoint
-        int base = tid - lane;
-        RawProp cur = base < n ? load_raw<PACKED>(props, base + lane, props_in_smem) : RawProp{};
-        for (; base < n; base += T) {
-          const RawProp nxt = base + T < n ? load_raw<PACKED>(props, base + T + lane, props_in_smem) : RawProp{};
-          int op, x, y, z;
-          decode_raw<PACKED>(cur, op, x, y, z);
-          int b, wsticky = 0;          // wsticky is warp-uniform: every exit below is taken by the whole warp
-          bool again;
-          do {
-            b = deduce(store, op, x, y, z, narrowed);
-            const int wb = __reduce_or_sync(0xffffffffu, b);
-            wsticky |= wb;
-            ++deductions_wac1;
-            again = (wb & F_CHANGED) && !(wb & F_FAILED);
-            __syncwarp();
-          } while (again);
-          bits |= (wsticky & (F_CHANGED | F_FAILED)) | (b & F_NOT_ENTAILED);
-          if (wsticky & F_FAILED) break;
-          cur = nxt;
-        }
-      } else {
-        int i = tid;
-        RawProp cur = i < n ? load_raw<PACKED>(props, i, props_in_smem) : RawProp{};
-        for (; i < n; i += T) {
-          const RawProp nxt = i + T < n ? load_raw<PACKED>(props, i + T, props_in_smem) : RawProp{};
-          int op, x, y, z;
-          decode_raw<PACKED>(cur, op, x, y, z);
-          bits |= deduce(store, op, x, y, z, narrowed);
-          cur = nxt;
-        }
-      }
+      Walk w;
+      w.ch = warp; w.evals = w.late_chg = w.pad_evals = 0; w.failed = 0; w.notent = 0;
+      w.widx = warp * 32 + lane;
+      w.cur = load_word(w.widx);
+      w.widx += nwarps * 32;
+#define TB_SWEEP(CLS) if (!w.failed) sweep_class<CLS>(w, wac1, nwarps);
+      TB_SWEEP(TBC_ADD_S) TB_SWEEP(TBC_ADD_XK) TB_SWEEP(TBC_ADD_ZK) TB_SWEEP(TBC_ADD_G)
+      TB_SWEEP(TBC_MUL) TB_SWEEP(TBC_TDIV) TB_SWEEP(TBC_TMOD) TB_SWEEP(TBC_MIN) TB_SWEEP(TBC_MAX)
+      TB_SWEEP(TBC_EQ_S) TB_SWEEP(TBC_EQ_T) TB_SWEEP(TBC_EQ_F) TB_SWEEP(TBC_EQ_ZK) TB_SWEEP(TBC_EQ_G)
+      TB_SWEEP(TBC_LEQ_S) TB_SWEEP(TBC_LEQ_T) TB_SWEEP(TBC_LEQ_F) TB_SWEEP(TBC_LEQ_ZK) TB_SWEEP(TBC_LEQ_G)
+#undef TB_SWEEP
+      deductions += (unsigned long long)w.evals * 32ull - (unsigned long long)w.pad_evals;
+      // a visit changed something iff it took more than one evaluation (WAC1) or ended on a change
+      const unsigned visits = (unsigned)(w.ch - warp) / (unsigned)nwarps + (w.failed ? 1u : 0u);
+      const bool changed = w.evals + w.late_chg > visits;
+      int bits = (changed ? F_CHANGED : 0) | (w.failed ? F_FAILED : 0) | (w.notent ? F_NOT_ENTAILED : 0);
       bits = __reduce_or_sync(0xffffffffu, bits);
       const int slot = it % 3;
       if (lane == 0 && bits) atomicOr(&c.flags[slot], bits);
@@ -352,13 +373,12 @@ struct Ctx {
   // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
   // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
   __device__ void propagate() {
-    
     unsigned long long t0 = 0;
     if (tid == 0) t0 = globaltimer_ns();
     int iters = 0, f;
-    bool obj_empty = false;
-    if (P.obj_var >= 0) { int l, u; store.ld(P.obj_var, l, u); obj_empty = l > u; }
-    if (obj_empty) f = F_FAILED;
+    bool pre_failed = P.root_failed != 0;       // a referenced variable is already empty in the root store
+    if (P.obj_var >= 0) { int l, u; store.ld(P.obj_var, l, u); pre_failed |= l > u; }
+    if (pre_failed) f = F_FAILED;
     else f = fixpoint(iters);
     const bool failed = (f & F_FAILED) != 0;
     const bool solution = !failed && !(f & F_NOT_ENTAILED);
@@ -405,8 +425,6 @@ struct Ctx {
         c.stop = 1;
       }
     }
-    if (!(P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold) && tid == 0)
-      st->deductions += (unsigned long long)iters * (unsigned long long)P.nprops;
     sync();
   }
 
@@ -600,8 +618,8 @@ __device__ __forceinline__ Ctl* shared_ctl(Ctl* local) {
   return (Ctl*)r;
 }
 
-template <int MEM, bool AOS, bool PACKED>
-__device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, Ctl* local, unsigned char* dyn) {
+template <int MEM>
+__device__ __forceinline__ void ctx_init(Ctx<MEM>& k, Ctl* local, unsigned char* dyn) {
   const DevParams& P = k.P;
   k.lc = local;
   if (MEM == TB_MEM_STORE_CLUSTER) {
@@ -617,11 +635,11 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, Ctl* local, u
   const int slot = k.slot;
   const size_t store_bytes = (size_t)P.vpad * 8;
   init_store_ref(k.store, P, dyn, slot);
-  k.props = P.props;
-  k.props_in_smem = false;
+  k.sdyn = dyn;
+  k.words = P.words;
   k.mbar_phase = 0;
   k.narrowed = 0;
-  k.deductions_wac1 = 0;
+  k.deductions = 0;
   k.g_root = P.block_root + (size_t)slot * 2 * P.vpad;
   k.g_best = P.block_best + (size_t)slot * 2 * P.vpad;
   k.dec = P.decisions + (size_t)slot * P.max_depth;
@@ -639,27 +657,26 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, AOS, PACKED>& k, Ctl* local, u
   if (MEM == TB_MEM_TCN_SHARED) {
     // stage the propagator table once: TMA bulk copy global -> shared
     unsigned char* sprops = dyn + store_bytes;
-    const unsigned bytes = (unsigned)((size_t)P.nprops_pad * (PACKED ? 8 : 16));
+    const unsigned bytes = (unsigned)((size_t)P.nchunks * 32 * 8);
     if (threadIdx.x == 0 && bytes) {
       fence_proxy_async();
       mbar_expect_tx(&local->mbar, bytes);
       for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-        bulk_g2s_issue(sprops + off, (const char*)P.props + off, min(BULK_CHUNK, bytes - off), &local->mbar);
+        bulk_g2s_issue(sprops + off, (const char*)P.words + off, min(BULK_CHUNK, bytes - off), &local->mbar);
     }
     if (bytes) { while (!mbar_try_wait(&local->mbar, k.mbar_phase)) {} k.mbar_phase ^= 1; }
-    k.props = sprops;
-    k.props_in_smem = true;
+    k.words = (const unsigned long long*)sprops;
   }
 }
 
-template <int MEM, bool AOS, bool PACKED>
-__device__ __forceinline__ void ctx_finish(Ctx<MEM, AOS, PACKED>& k) {
+template <int MEM>
+__device__ __forceinline__ void ctx_finish(Ctx<MEM>& k) {
   // fold the per-thread / per-warp counters into the block statistics
   unsigned n = k.narrowed;
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(&k.st->narrowed, (unsigned long long)n);
-    if (k.deductions_wac1) atomicAdd(&k.st->deductions, k.deductions_wac1 * 32ull);
+    if (k.deductions) atomicAdd(&k.st->deductions, k.deductions);
   }
   k.sync();        // with a cluster: nobody leaves while a peer may still touch its shared memory
 }
@@ -669,12 +686,12 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, AOS, PACKED>& k) {
 // ================================================================================================
 
 // The persistent dive-and-solve kernel (gpu_barebones_solve, barebones :620-901).
-template <int MEM, bool AOS, bool PACKED>
+template <int MEM>
 __global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ DevParams P) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM, AOS, PACKED> k(P, c);
+  Ctx<MEM> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid;
   BlockStats* st = k.st;
@@ -711,37 +728,46 @@ __global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ Dev
 }
 
 // One fixpoint per block on caller-provided stores (tb_propagate / tb_propagate_batch).
-template <int MEM, bool AOS, bool PACKED>
+template <int MEM>
 __global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__ DevParams P, int nstores,
                                                          const int* in_lb, const int* in_ub,
                                                          int* out_lb, int* out_ub, int* out_failed, int repeat) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM, AOS, PACKED> k(P, c);
+  Ctx<MEM> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid, T = k.T;
   for (int s = k.slot; s < nstores; s += k.nslots) {
     int f = 0, iters = 0;
     for (int r = 0; r < repeat; ++r) {
       k.sync();
-      for (int v = tid; v < P.vpad; v += T) {
-        int l = 0, u = 0;
-        if (v < P.nvars) { l = in_lb[(size_t)s * P.nvars + v]; u = in_ub[(size_t)s * P.nvars + v]; }
-        k.store.set(v, l, u);
-      }
+      // load the caller's store into the block store (slot order); a referenced variable that is already
+      // empty fails the store before any propagation, as the oracle's deduce does
+      if (tid == 0) c.leaf = 0;
       k.sync();
-      f = k.fixpoint(iters);
+      int empty_seen = 0;
+      for (int sl = tid; sl < P.vpad; sl += T) {
+        const int v = P.var_of[sl];
+        int l = 0, u = 0;
+        if (v >= 0) {
+          l = in_lb[(size_t)s * P.nvars + v]; u = in_ub[(size_t)s * P.nvars + v];
+          empty_seen |= (l > u) & (int)P.referenced[v];
+        }
+        k.store.set(sl, l, u);
+      }
+      if (empty_seen) atomicOr(&c.leaf, 1);
+      k.sync();
+      if (c.leaf) { f = F_FAILED; iters = 0; k.sync(); }
+      else f = k.fixpoint(iters);
       if (tid == 0) {
         k.st->fixpoint_iterations += (unsigned long long)iters;
         k.st->nodes++;
-        if (!(P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold))
-          k.st->deductions += (unsigned long long)iters * (unsigned long long)P.nprops;
       }
     }
     k.sync();
     for (int v = tid; v < P.nvars; v += T) {
-      int l, u; k.store.ld(v, l, u);
+      int l, u; k.store.ld(P.slot_of[v], l, u);
       out_lb[(size_t)s * P.nvars + v] = l; out_ub[(size_t)s * P.nvars + v] = u;
     }
     if (tid == 0) out_failed[s] = (f & F_FAILED) ? 1 : 0;
@@ -750,13 +776,13 @@ __global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__
 }
 
 // EPS dive only (tb_dive / tb_dive_batch).
-template <int MEM, bool AOS, bool PACKED>
+template <int MEM>
 __global__ void __launch_bounds__(1024) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
                                                     int depth, int* out_lb, int* out_ub, int* out_remaining, int* out_kind) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM, AOS, PACKED> k(P, c);
+  Ctx<MEM> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid, T = k.T;
   for (int s = k.slot; s < count; s += k.nslots) {
@@ -764,7 +790,7 @@ __global__ void __launch_bounds__(1024) dive_kernel(const __grid_constant__ DevP
     int remaining = k.dive(first + (unsigned long long)s, depth);
     k.sync();
     for (int v = tid; v < P.nvars; v += T) {
-      int l, u; k.store.ld(v, l, u);
+      int l, u; k.store.ld(P.slot_of[v], l, u);
       out_lb[(size_t)s * P.nvars + v] = l; out_ub[(size_t)s * P.nvars + v] = u;
     }
     if (tid == 0) { out_remaining[s] = remaining; out_kind[s] = c.leaf ? (c.failed ? 1 : 2) : 0; }
@@ -806,7 +832,8 @@ struct tb_solver {
   int device = 0;
   int nvars = 0, nprops = 0;
   int mem_kind = TB_MEM_GLOBAL, threads = 256, num_blocks = 1, blocks_per_sm = 1, cluster = 1;
-  bool aos = false, packed = true;
+  TnfLayout layout;                   // device table + variable placement (layout.h)
+  std::vector<int32_t> root_lb, root_ub;   // the root domains (precondition check of tb_propagate)
   size_t shared_bytes = 0, store_bytes = 0, prop_bytes = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
@@ -836,25 +863,16 @@ static tb_status dev_alloc(tb_solver* s, T** p, size_t count) {
   return TB_OK;
 }
 
-// kernel dispatch over (placement, store layout, propagator format)
+// kernel dispatch over the placement
 template <class F>
 static tb_status dispatch(const tb_solver* s, F&& f) {
-#define TB_CASE(M)                                                                                   \
-  case M:                                                                                            \
-    if (s->aos) { if (s->packed) return f(std::integral_constant<int, M>{}, std::true_type{}, std::true_type{});   \
-                  else return f(std::integral_constant<int, M>{}, std::true_type{}, std::false_type{}); }           \
-    else        { if (s->packed) return f(std::integral_constant<int, M>{}, std::false_type{}, std::true_type{});  \
-                  else return f(std::integral_constant<int, M>{}, std::false_type{}, std::false_type{}); }
   switch (s->mem_kind) {
-    TB_CASE(TB_MEM_GLOBAL)
-    TB_CASE(TB_MEM_STORE_SHARED)
-    TB_CASE(TB_MEM_TCN_SHARED)
-    case TB_MEM_STORE_CLUSTER:
-      if (s->packed) return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, std::false_type{}, std::true_type{});
-      else return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, std::false_type{}, std::false_type{});
+    case TB_MEM_GLOBAL: return f(std::integral_constant<int, TB_MEM_GLOBAL>{});
+    case TB_MEM_STORE_SHARED: return f(std::integral_constant<int, TB_MEM_STORE_SHARED>{});
+    case TB_MEM_TCN_SHARED: return f(std::integral_constant<int, TB_MEM_TCN_SHARED>{});
+    case TB_MEM_STORE_CLUSTER: return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{});
     default: break;
   }
-#undef TB_CASE
   set_error("unsupported memory kind");
   return TB_ERR_UNSUPPORTED;
 }
@@ -879,6 +897,13 @@ static cudaError_t launch_workers(const tb_solver* s, void (*kernel)(KArgs...), 
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
+}
+
+// The sweep assigns chunk ch to warp (ch mod nwarps) with a mask: the warp count is a power of two.
+static int pow2_threads(int t) {
+  int p = 32;
+  while (p * 2 <= std::min(t, 1024)) p *= 2;
+  return p;
 }
 
 // Placement policy: MemoryConfig (memory_gpu.hpp:43-84) + configure_gpu_barebones (barebones :527-606),
@@ -928,7 +953,7 @@ static tb_status configure(tb_solver* s) {
     s->store_bytes = (size_t)s->P.vpad * 8;
     s->mem_kind = kind;
     s->shared_bytes = (size_t)s->P.vc * 8;
-    s->threads = s->opt.threads_per_block > 0 ? std::max(32, std::min(1024, (s->opt.threads_per_block + 31) / 32 * 32)) : 1024;
+    s->threads = s->opt.threads_per_block > 0 ? pow2_threads(s->opt.threads_per_block) : 1024;
     s->blocks_per_sm = 1;
     // how many clusters can be co-resident is asked from the driver once the kernel attributes are set
     s->num_blocks = std::max(1, s->num_sms / cluster);
@@ -943,9 +968,9 @@ static tb_status configure(tb_solver* s) {
     bps = std::min(bps, 8);
     threads = bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024);
     // do not use more threads than there is work per sweep
-    while (threads > 128 && threads / 2 >= s->P.nprops_pad) threads /= 2;
+    while (threads > 128 && threads / 2 >= s->P.nchunks * 32) threads /= 2;
   }
-  threads = std::max(32, std::min(1024, (threads + 31) / 32 * 32));
+  threads = pow2_threads(threads);
   bps = std::max(1, std::min(bps, 2048 / threads));
   s->threads = threads;
   s->blocks_per_sm = bps;
@@ -957,18 +982,18 @@ static tb_status configure(tb_solver* s) {
 }
 
 static tb_status set_smem_attr(tb_solver* s) {
-  return dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    constexpr int m = decltype(M)::value; constexpr bool a = decltype(A)::value; constexpr bool k = decltype(K)::value;
+  return dispatch(s, [&](auto M) -> tb_status {
+    constexpr int m = decltype(M)::value;
     if (s->shared_bytes) {
-      CU(cudaFuncSetAttribute(solve_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
-      CU(cudaFuncSetAttribute(propagate_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
-      CU(cudaFuncSetAttribute(dive_kernel<m, a, k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(solve_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(propagate_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(dive_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
     }
     if (m == TB_MEM_STORE_CLUSTER) {
       if (s->cluster > 8) {
-        CU(cudaFuncSetAttribute(solve_kernel<m, a, k>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU(cudaFuncSetAttribute(propagate_kernel<m, a, k>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU(cudaFuncSetAttribute(dive_kernel<m, a, k>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(solve_kernel<m>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(propagate_kernel<m>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(dive_kernel<m>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       }
       cudaLaunchConfig_t cfg = {};
       cfg.blockDim = dim3((unsigned)s->threads);
@@ -979,7 +1004,7 @@ static tb_status set_smem_attr(tb_solver* s) {
       attr[0].val.clusterDim.x = (unsigned)s->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int nclusters = 0;
-      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m, a, k>, &cfg));
+      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m>, &cfg));
       if (nclusters < 1) { set_error("the device cannot host a cluster of this size"); return TB_ERR_UNSUPPORTED; }
       int workers = nclusters;
       if (s->opt.or_blocks > 0) workers = std::min(workers, s->opt.or_blocks);
@@ -1044,8 +1069,6 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   memset(&P, 0, sizeof(P));
   s->nvars = pb->nvars; s->nprops = pb->nprops;
   P.nvars = pb->nvars; P.nprops = pb->nprops;
-  P.vpad = std::max(4, (pb->nvars + 3) / 4 * 4);
-  P.nprops_pad = (pb->nprops + 31) / 32 * 32;
   P.obj_var = pb->obj_var;
   P.has_eps_strategy = pb->has_eps_strategy;
   P.fixpoint_kind = opt.fixpoint == TB_FP_AC1 ? TB_FP_AC1 : TB_FP_WAC1;
@@ -1053,11 +1076,39 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   P.cutnodes = opt.cutnodes;
   P.rank = opt.gpu_rank; P.world = opt.gpu_world;
   P.max_depth = opt.max_depth > 0 ? opt.max_depth : 10000;
-  s->packed = pb->nvars <= (1 << 20) && env_int("TB_PROP_FORMAT16", 0) == 0;
-  s->aos = env_int("TB_STORE_AOS", 0) != 0;
-  s->store_bytes = (size_t)P.vpad * 8;
-  s->prop_bytes = (size_t)P.nprops_pad * (s->packed ? 8 : 16);
+  if (pb->nvars > TBC_MAX_VARS) { set_error("more than 2^21 variables: the device propagator word has 21-bit fields"); return fail(TB_ERR_UNSUPPORTED); }
+  s->root_lb.assign(pb->lb, pb->lb + pb->nvars);
+  s->root_ub.assign(pb->ub, pb->ub + pb->nvars);
+
+  // ---- placement, then the layout pass for that placement (layout.h) ----------------------------------
+  {
+    // sizes the placement policy needs: the table is padded per class to whole chunks of 32
+    int per_class[TBC_NUM] = {0};
+    for (int i = 0; i < pb->nprops; ++i) { bool sw; ++per_class[tb_classify(pb->props[i], pb->lb, pb->ub, &sw)]; }
+    int nchunks = 0;
+    for (int c = 0; c < TBC_NUM; ++c) nchunks += (per_class[c] + 31) / 32;
+    P.nchunks = nchunks;
+    s->prop_bytes = (size_t)nchunks * 32 * 8;
+    s->store_bytes = (size_t)std::max(32, (pb->nvars + 31) / 32 * 32) * 8;     // shared placements pad to the 32 banks
+  }
   if ((rc = configure(s)) != TB_OK) return fail(rc);
+  {
+    TnfLayoutOptions lo;
+    const bool shared_store = s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED;
+    lo.nbanks = shared_store && env_int("TB_NO_BANK_LAYOUT", 0) == 0 ? 16 : 0;
+    lo.slot_align = shared_store ? 32 : (s->mem_kind == TB_MEM_STORE_CLUSTER ? 4 * s->cluster : 4);
+    std::string err;
+    if ((rc = tb_build_layout(pb, lo, &s->layout, &err)) != TB_OK) { set_error(err); return fail(rc); }
+    const TnfLayout& L = s->layout;
+    P.vpad = L.nslots;
+    if (s->mem_kind == TB_MEM_STORE_CLUSTER && P.vpad != P.vc * s->cluster) { set_error("internal: cluster slice size mismatch"); return fail(TB_ERR_INVALID); }
+    s->store_bytes = (size_t)P.vpad * 8;
+    P.nchunks = L.cls_begin[TBC_NUM];
+    for (int c = 0; c <= TBC_NUM; ++c) P.cls_begin[c] = L.cls_begin[c];
+    for (int c = 0; c < TBC_NUM; ++c) P.cls_last[c] = L.cls_last[c];
+    if (pb->obj_var >= 0) P.obj_var = L.slot_of[pb->obj_var];
+    for (int v = 0; v < pb->nvars; ++v) if (L.referenced[v] && pb->lb[v] > pb->ub[v]) P.root_failed = 1;
+  }
   if ((rc = set_smem_attr(s)) != TB_OK) return fail(rc);
 
   // ---- device images ---------------------------------------------------------------------------------
@@ -1069,41 +1120,43 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (cudaMemcpy(d, img.data(), img.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D root store"); return fail(TB_ERR_CUDA); }
     P.root_store = d;
   }
-  // Layout of the propagator table: inside every window of `threads` consecutive propagators (the ones
-  // a block evaluates concurrently in one step of a sweep) group equal operators together so that a
-  // warp's 32 lanes mostly run the same operator. The fixpoint does not depend on the order.
-  std::vector<tb_prop> ordered(pb->props, pb->props + pb->nprops);
-  if (env_int("TB_NO_OP_GROUPING", 0) == 0)
-    for (size_t w0 = 0; w0 < ordered.size(); w0 += (size_t)s->threads)
-      std::stable_sort(ordered.begin() + w0, ordered.begin() + std::min(ordered.size(), w0 + (size_t)s->threads),
-                       [](const tb_prop& a, const tb_prop& b) { return a.op < b.op; });
-  if (s->packed) {
-    std::vector<unsigned long long> w((size_t)P.nprops_pad, (unsigned long long)TB_OP_NOP << 60);
-    for (int i = 0; i < pb->nprops; ++i) {
-      const tb_prop& p = ordered[i];
-      w[i] = ((unsigned long long)p.op << 60) | ((unsigned long long)p.x << 40) | ((unsigned long long)p.y << 20) | (unsigned long long)p.z;
-    }
+  {
+    const TnfLayout& L = s->layout;
     unsigned long long* d = nullptr;
-    if ((rc = dev_alloc(s, &d, w.size()))) return fail(rc);
-    if (w.size() && cudaMemcpy(d, w.data(), w.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
-    P.props = d;
-  } else {
-    std::vector<tb_prop> w((size_t)P.nprops_pad, tb_prop{TB_OP_NOP, 0, 0, 0});
-    for (int i = 0; i < pb->nprops; ++i) w[i] = ordered[i];
-    tb_prop* d = nullptr;
-    if ((rc = dev_alloc(s, &d, w.size()))) return fail(rc);
-    if (w.size() && cudaMemcpy(d, w.data(), w.size() * sizeof(tb_prop), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
-    P.props = d;
+    // 32 chunks of padding behind the table: a warp prefetches its next chunk without a bound check
+    if ((rc = dev_alloc(s, &d, L.words.size() + 32 * 32))) return fail(rc);
+    if (cudaMemset(d, 0, (L.words.size() + 32 * 32) * 8) != cudaSuccess ||
+        (L.words.size() && cudaMemcpy(d, L.words.data(), L.words.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
+    P.words = d;
+    std::vector<int> var_of((size_t)P.vpad, -1);
+    for (int v = 0; v < pb->nvars; ++v) var_of[L.slot_of[v]] = v;
+    int *dslot = nullptr, *dvar = nullptr;
+    unsigned char* dref = nullptr;
+    if ((rc = dev_alloc(s, &dslot, L.slot_of.size()))) return fail(rc);
+    if ((rc = dev_alloc(s, &dvar, var_of.size()))) return fail(rc);
+    if ((rc = dev_alloc(s, &dref, L.referenced.size()))) return fail(rc);
+    if ((pb->nvars && cudaMemcpy(dslot, L.slot_of.data(), L.slot_of.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) ||
+        cudaMemcpy(dvar, var_of.data(), var_of.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        (pb->nvars && cudaMemcpy(dref, L.referenced.data(), L.referenced.size(), cudaMemcpyHostToDevice) != cudaSuccess)) {
+      set_error("H2D layout tables"); return fail(TB_ERR_CUDA);
+    }
+    P.slot_of = dslot; P.var_of = dvar; P.referenced = dref;
   }
   {
     std::vector<DevStrategy> hs((size_t)std::max(1, pb->nstrategies));
+    const TnfLayout& L = s->layout;
     for (int i = 0; i < pb->nstrategies; ++i) {
       const tb_strategy& st = pb->strategies[i];
       hs[i].var_order = st.var_order; hs[i].val_order = st.val_order; hs[i].n = st.n; hs[i].vars = nullptr;
-      if (st.n) {
+      // the device works on slots: translate the list; "all variables in index order" (n == 0) becomes an
+      // explicit list once the placement is not the identity, so that ties still break on the caller's order
+      std::vector<int> slots;
+      if (st.n) { slots.resize((size_t)st.n); for (int j = 0; j < st.n; ++j) slots[j] = L.slot_of[st.vars[j]]; }
+      else if (!L.identity && pb->nvars) { slots = L.slot_of; hs[i].n = pb->nvars; }
+      if (!slots.empty()) {
         int* dv = nullptr;
-        if ((rc = dev_alloc(s, &dv, (size_t)st.n))) return fail(rc);
-        if (cudaMemcpy(dv, st.vars, (size_t)st.n * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D strategy"); return fail(TB_ERR_CUDA); }
+        if ((rc = dev_alloc(s, &dv, slots.size()))) return fail(rc);
+        if (cudaMemcpy(dv, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D strategy"); return fail(TB_ERR_CUDA); }
         hs[i].vars = dv;
       }
     }
@@ -1206,15 +1259,14 @@ static void reduce_stats(const std::vector<BlockStats>& bs, tb_stats* st, int* b
   if (best_block) *best_block = best;
 }
 
-// Position of lb[v] / ub[v] inside a store image (SoA, AoS pairs, or cluster slices lb[vc]|ub[vc] per CTA).
+// Position of lb[v] / ub[v] inside a store image: slot = layout.slot_of[v]; one {lb, ub} pair per slot, or
+// cluster slices of vc pairs per CTA with slot s in CTA (s mod C) at local index (s div C).
 static inline size_t img_lb(const tb_solver* s, int v) {
-  if (s->mem_kind == TB_MEM_STORE_CLUSTER) { const int c = s->cluster, vc = s->P.vc; return (size_t)(v % c) * 2 * vc + (size_t)(v / c); }
-  return s->aos ? (size_t)2 * v : (size_t)v;
+  const int sl = s->layout.slot_of[v];
+  if (s->mem_kind == TB_MEM_STORE_CLUSTER) { const int c = s->cluster, vc = s->P.vc; return (size_t)(sl % c) * 2 * vc + 2 * (size_t)(sl / c); }
+  return 2 * (size_t)sl;
 }
-static inline size_t img_ub(const tb_solver* s, int v) {
-  if (s->mem_kind == TB_MEM_STORE_CLUSTER) { const int c = s->cluster, vc = s->P.vc; return (size_t)(v % c) * 2 * vc + vc + (size_t)(v / c); }
-  return s->aos ? (size_t)2 * v + 1 : (size_t)s->P.vpad + v;
-}
+static inline size_t img_ub(const tb_solver* s, int v) { return img_lb(s, v) + 1; }
 static void unpack_store(const tb_solver* s, const int* img, int32_t* lb, int32_t* ub) {
   for (int v = 0; v < s->nvars; ++v) { lb[v] = img[img_lb(s, v)]; ub[v] = img[img_ub(s, v)]; }
 }
@@ -1253,8 +1305,8 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   CU(cudaMemcpyAsync(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->d_next, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
-  rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    CU(launch_workers(s, solve_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>, s->num_blocks, P));
+  rc = dispatch(s, [&](auto M) -> tb_status {
+    CU(launch_workers(s, solve_kernel<decltype(M)::value>, s->num_blocks, P));
     CU(cudaGetLastError());
     return TB_OK;
   });
@@ -1328,12 +1380,20 @@ extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int
   const int32_t *hl = lb_in, *hu = ub_in;
   if (!lb_in || !ub_in) {          // NULL = the root store, replicated
     tmp.resize(2 * cells);
-    std::vector<int> img((size_t)2 * s->P.vpad);
-    CU(cudaMemcpy(img.data(), s->P.root_store, img.size() * sizeof(int), cudaMemcpyDeviceToHost));
-    std::vector<int32_t> rl(nv), ru(nv);
-    unpack_store(s, img.data(), rl.data(), ru.data());
-    for (int b = 0; b < nstores; ++b) { std::copy(rl.begin(), rl.end(), tmp.begin() + b * nv); std::copy(ru.begin(), ru.end(), tmp.begin() + cells + b * nv); }
+    for (int b = 0; b < nstores; ++b) {
+      std::copy(s->root_lb.begin(), s->root_lb.end(), tmp.begin() + b * nv);
+      std::copy(s->root_ub.begin(), s->root_ub.end(), tmp.begin() + cells + b * nv);
+    }
     hl = tmp.data(); hu = tmp.data() + cells;
+  } else {
+    // Precondition: every store is contained in the root store the solver was created with (the device
+    // table is specialised on the root domains: constants are folded, 32-bit arithmetic is proven exact).
+    for (int b = 0; b < nstores; ++b)
+      for (size_t v = 0; v < nv; ++v)
+        if (lb_in[b * nv + v] < s->root_lb[v] || ub_in[b * nv + v] > s->root_ub[v]) {
+          set_error("tb_propagate: store " + std::to_string(b) + " is not contained in the root store (variable " + std::to_string(v) + ")");
+          return TB_ERR_INVALID;
+        }
   }
   if (cells) {
     CU(cudaMemcpyAsync(s->d_in_lb, hl, cells * sizeof(int), cudaMemcpyHostToDevice, s->stream));
@@ -1341,8 +1401,8 @@ extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int
   }
   const int repeat = std::max(1, s->opt.propagate_repeat);
   CU(cudaEventRecord(s->ev_start, s->stream));
-  rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    CU(launch_workers(s, propagate_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>, grid, s->P, nstores,
+  rc = dispatch(s, [&](auto M) -> tb_status {
+    CU(launch_workers(s, propagate_kernel<decltype(M)::value>, grid, s->P, nstores,
                       (const int*)s->d_in_lb, (const int*)s->d_in_ub, s->d_out_lb, s->d_out_ub, s->d_out_i0, repeat));
     CU(cudaGetLastError());
     return TB_OK;
@@ -1388,8 +1448,8 @@ extern "C" tb_status tb_dive_batch(tb_solver* s, uint64_t first, int32_t count, 
   DevParams P = s->P;
   P.cutnodes = 0;
   P.t_start = 0;
-  rc = dispatch(s, [&](auto M, auto A, auto K) -> tb_status {
-    CU(launch_workers(s, dive_kernel<decltype(M)::value, decltype(A)::value, decltype(K)::value>, grid, P,
+  rc = dispatch(s, [&](auto M) -> tb_status {
+    CU(launch_workers(s, dive_kernel<decltype(M)::value>, grid, P,
                       (unsigned long long)first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1));
     CU(cudaGetLastError());
     return TB_OK;

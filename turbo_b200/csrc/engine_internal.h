@@ -1,6 +1,7 @@
 // engine_internal.h — POD structures shared between the host driver and the kernels.
 #pragma once
 #include <stdint.h>
+#include "tnf_classes.h"
 
 // One entry of the per-block decision stack: LightBranch<Itv>
 // (reference include/barebones_dive_and_solve.hpp:135,358-393). 32 bytes.
@@ -27,8 +28,14 @@ struct BlockStats {
 // Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
 // flattened to plain device pointers (no managed memory, no device-side malloc).
 struct DevParams {
-  int nvars, vpad, nprops, nprops_pad;
-  const void* props;            // packed u64 or int4 table, padded with NOPs to a multiple of 32
+  int nvars, vpad, nprops, nchunks;
+  const unsigned long long* words;  // class-sorted device propagator table, nchunks * 32 words (tnf_classes.h)
+  int cls_begin[TBC_NUM + 1];   // first chunk of each class
+  int cls_last[TBC_NUM];        // real propagators in the last chunk of each class
+  const int* slot_of;           // variable -> slot of the store image (layout.h)
+  const int* var_of;            // slot -> variable, -1 for padding slots
+  const unsigned char* referenced;  // per variable: appears in some propagator
+  int root_failed, pad1_;       // a referenced variable is empty in the root store
   const int* root_store;        // image of the root store, same layout as a block store
   int nstrategies, has_eps_strategy, obj_var, fixpoint_kind, wac1_threshold, subproblems_power;
   const DevStrategy* strategies;

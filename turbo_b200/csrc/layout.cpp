@@ -1,0 +1,242 @@
+// layout.cpp — see layout.h.
+#include "layout.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace {
+
+inline bool is_small(const int32_t* lb, const int32_t* ub, int v) {
+  return lb[v] >= -TBC_SMALL_LIMIT && ub[v] <= TBC_SMALL_LIMIT;
+}
+inline bool is_fixed(const int32_t* lb, const int32_t* ub, int v) { return lb[v] == ub[v]; }
+// a root constant whose value fits a 21-bit field
+inline bool is_fieldk(const int32_t* lb, const int32_t* ub, int v) {
+  return lb[v] == ub[v] && lb[v] >= -TBC_CONST_LIMIT && lb[v] < TBC_CONST_LIMIT;
+}
+
+struct Item { int cls; int x, y, z; };   // x/z may hold a constant depending on the class
+
+inline bool loads_x(int c) { return !(c == TBC_ADD_XK || c == TBC_EQ_T || c == TBC_EQ_F || c == TBC_LEQ_T || c == TBC_LEQ_F); }
+inline bool loads_z(int c) { return !(c == TBC_ADD_ZK || c == TBC_EQ_ZK || c == TBC_LEQ_ZK); }
+
+}  // namespace
+
+const char* tb_class_name(int cls) {
+  static const char* names[TBC_NUM] = {"add_s", "add_xk", "add_zk", "add_g", "mul", "tdiv", "tmod", "min", "max",
+                                       "eq_s", "eq_t", "eq_f", "eq_zk", "eq_g", "leq_s", "leq_t", "leq_f", "leq_zk", "leq_g"};
+  return cls >= 0 && cls < TBC_NUM ? names[cls] : "?";
+}
+
+int tb_classify(const tb_prop& p, const int32_t* lb, const int32_t* ub, bool* swap_yz) {
+  *swap_yz = false;
+  const bool sx = is_small(lb, ub, p.x), sy = is_small(lb, ub, p.y), sz = is_small(lb, ub, p.z);
+  switch (p.op) {
+    case TB_OP_ADD:
+      if (!(sx && sy && sz)) return TBC_ADD_G;
+      if (is_fieldk(lb, ub, p.x)) return TBC_ADD_XK;
+      if (is_fieldk(lb, ub, p.z)) return TBC_ADD_ZK;
+      if (is_fieldk(lb, ub, p.y)) { *swap_yz = true; return TBC_ADD_ZK; }
+      return TBC_ADD_S;
+    case TB_OP_MUL: return TBC_MUL;
+    case TB_OP_TDIV: return TBC_TDIV;
+    case TB_OP_TMOD: return TBC_TMOD;
+    case TB_OP_MIN: return TBC_MIN;
+    case TB_OP_MAX: return TBC_MAX;
+    case TB_OP_EQ:
+      if (!(sy && sz)) return TBC_EQ_G;
+      if (is_fixed(lb, ub, p.x) && lb[p.x] == 1) return TBC_EQ_T;
+      if (is_fixed(lb, ub, p.x) && lb[p.x] == 0) return TBC_EQ_F;
+      if (is_fieldk(lb, ub, p.z)) return TBC_EQ_ZK;
+      if (is_fieldk(lb, ub, p.y)) { *swap_yz = true; return TBC_EQ_ZK; }
+      return TBC_EQ_S;
+    default:   // TB_OP_LEQ
+      if (!(sy && sz)) return TBC_LEQ_G;
+      if (is_fixed(lb, ub, p.x) && lb[p.x] == 1) return TBC_LEQ_T;
+      if (is_fixed(lb, ub, p.x) && lb[p.x] == 0) return TBC_LEQ_F;
+      if (is_fieldk(lb, ub, p.z)) return TBC_LEQ_ZK;
+      return TBC_LEQ_S;
+  }
+}
+
+tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, TnfLayout* out, std::string* err) {
+  const int V = pb->nvars, P = pb->nprops;
+  if (V > TBC_MAX_VARS) {
+    if (err) *err = "more than 2^21 variables: the device propagator word has 21-bit fields";
+    return TB_ERR_UNSUPPORTED;
+  }
+  TnfLayout& L = *out;
+  L = TnfLayout();
+  L.nvars = V;
+  int align = std::max(1, opt.slot_align);
+  if (opt.nbanks > 0) align = std::max(align, opt.nbanks);
+  L.nslots = std::max(align, (V + align - 1) / align * align);
+  L.referenced.assign((size_t)V, 0);
+
+  // ---- classify, sort by class (stable: the ternariser's order carries the model's locality) ---------------
+  std::vector<Item> items((size_t)P);
+  for (int i = 0; i < P; ++i) {
+    const tb_prop& p = pb->props[i];
+    bool swap = false;
+    Item it;
+    it.cls = tb_classify(p, pb->lb, pb->ub, &swap);
+    it.x = p.x; it.y = swap ? p.z : p.y; it.z = swap ? p.y : p.z;
+    items[(size_t)i] = it;
+    L.referenced[p.x] = L.referenced[p.y] = L.referenced[p.z] = 1;
+  }
+  std::vector<int> order((size_t)P);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
+
+  // chunk table: indices into `items`, -1 = padding (filled with a copy of the class's last propagator)
+  std::vector<int> lanes;
+  lanes.reserve((size_t)P + 32 * TBC_NUM);
+  {
+    size_t i = 0;
+    for (int c = 0; c < TBC_NUM; ++c) {
+      L.cls_begin[c] = (int)(lanes.size() / 32);
+      size_t n = 0;
+      while (i < order.size() && items[order[i]].cls == c) { lanes.push_back(order[i]); ++i; ++n; }
+      L.cls_last[c] = n ? (int)((n - 1) % 32 + 1) : 0;
+      while (lanes.size() % 32) lanes.push_back(-1);
+    }
+    L.cls_begin[TBC_NUM] = (int)(lanes.size() / 32);
+  }
+  const int nchunks = L.cls_begin[TBC_NUM];
+
+  // ---- variable placement --------------------------------------------------------------------------------
+  L.slot_of.resize((size_t)V);
+  std::iota(L.slot_of.begin(), L.slot_of.end(), 0);
+  L.identity = true;
+  // role sets: for every chunk and every loaded operand position, the distinct variables the 32 lanes read
+  std::vector<std::vector<int>> sets;
+  if (nchunks) sets.reserve((size_t)nchunks * 6);
+  // (a 64-bit shared-memory load is served one half-warp at a time: lanes_per_set = 16)
+  const int LPS = opt.lanes_per_set > 0 ? opt.lanes_per_set : 32;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int cls = items[lanes[(size_t)ch * 32]].cls;
+    for (int role = 0; role < 3; ++role) {
+      if ((role == 0 && !loads_x(cls)) || (role == 2 && !loads_z(cls))) continue;
+      L.loads_per_sweep += (uint64_t)(ch + 1 == L.cls_begin[cls + 1] ? L.cls_last[cls] : 32);
+      for (int l0 = 0; l0 < 32; l0 += LPS) {
+        std::vector<int> vs;
+        for (int l = l0; l < l0 + LPS; ++l) {
+          const int id = lanes[(size_t)ch * 32 + l];
+          if (id < 0) continue;
+          const Item& it = items[id];
+          vs.push_back(role == 0 ? it.x : (role == 1 ? it.y : it.z));
+        }
+        if (vs.empty()) continue;
+        std::sort(vs.begin(), vs.end());
+        vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+        sets.push_back(std::move(vs));
+      }
+    }
+  }
+  if (opt.nbanks > 0 && V > 0) {
+    const int NB = opt.nbanks;
+    // membership lists
+    std::vector<int> deg((size_t)V, 0);
+    for (const auto& s : sets) for (int v : s) ++deg[v];
+    std::vector<size_t> off((size_t)V + 1, 0);
+    for (int v = 0; v < V; ++v) off[v + 1] = off[v] + (size_t)deg[v];
+    std::vector<int> memb(off[V]);
+    {
+      std::vector<size_t> fill(off.begin(), off.end() - 1);
+      for (size_t s = 0; s < sets.size(); ++s) for (int v : sets[s]) memb[fill[v]++] = (int)s;
+    }
+    std::vector<uint16_t> cnt(sets.size() * (size_t)NB, 0);
+    std::vector<uint16_t> mx(sets.size(), 0);
+    std::vector<int> pop((size_t)NB, 0);
+    const int cap = L.nslots / NB;
+    std::vector<int> bank((size_t)V, 0);
+    std::vector<int> vorder((size_t)V);
+    std::iota(vorder.begin(), vorder.end(), 0);
+    std::stable_sort(vorder.begin(), vorder.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+    std::vector<long long> score((size_t)NB);
+    for (int v : vorder) {
+      std::fill(score.begin(), score.end(), 0);
+      for (size_t k = off[v]; k < off[v + 1]; ++k) {
+        const uint16_t* c = &cnt[(size_t)memb[k] * NB];
+        const uint16_t m = mx[memb[k]];
+        for (int b = 0; b < NB; ++b) score[b] += (c[b] + 1 > m ? 4096 : 0) + c[b];
+      }
+      int best = -1;
+      for (int b = 0; b < NB; ++b) {
+        if (pop[b] >= cap) continue;
+        if (best < 0 || score[b] < score[best] || (score[b] == score[best] && pop[b] < pop[best])) best = b;
+      }
+      bank[v] = best;
+      ++pop[best];
+      for (size_t k = off[v]; k < off[v + 1]; ++k) {
+        uint16_t& c = cnt[(size_t)memb[k] * NB + best];
+        ++c;
+        if (c > mx[memb[k]]) mx[memb[k]] = c;
+      }
+    }
+    // slots: bank b owns b, b + NB, b + 2 NB, ...
+    std::vector<int> next((size_t)NB);
+    std::iota(next.begin(), next.end(), 0);
+    for (int v = 0; v < V; ++v) { L.slot_of[v] = next[bank[v]]; next[bank[v]] += NB; }
+    L.identity = true;
+    for (int v = 0; v < V; ++v) if (L.slot_of[v] != v) { L.identity = false; break; }
+  }
+  // bank model: wavefronts per set (one set = the lanes served together)
+  {
+    const int NB = opt.nbanks > 0 ? opt.nbanks : (LPS == 16 ? 16 : 32);
+    unsigned long long wf = 0;
+    std::vector<int> c((size_t)NB);
+    for (const auto& s : sets) {
+      std::fill(c.begin(), c.end(), 0);
+      int m = 0;
+      for (int v : s) m = std::max(m, ++c[L.slot_of[v] % NB]);
+      wf += (unsigned long long)m;
+    }
+    L.wavefronts_per_load = sets.empty() ? 0.0 : (double)wf / (double)sets.size();
+  }
+
+  // ---- device words ------------------------------------------------------------------------------------------
+  L.words.assign(lanes.size(), 0);
+  uint64_t last_word = 0;
+  for (size_t i = 0; i < lanes.size(); ++i) {
+    if (lanes[i] < 0) { L.words[i] = last_word; continue; }
+    const Item& it = items[lanes[i]];
+    uint64_t f0, f1, f2;
+    if (loads_x(it.cls)) f0 = (uint64_t)L.slot_of[it.x];
+    else if (it.cls == TBC_ADD_XK) f0 = (uint64_t)((uint32_t)pb->lb[it.x] & TBC_FIELD_MASK);
+    else f0 = 0;
+    f1 = (uint64_t)L.slot_of[it.y];
+    if (loads_z(it.cls)) f2 = (uint64_t)L.slot_of[it.z];
+    else f2 = (uint64_t)((uint32_t)pb->lb[it.z] & TBC_FIELD_MASK);
+    last_word = f0 | (f1 << TBC_FIELD_BITS) | (f2 << (2 * TBC_FIELD_BITS));
+    L.words[i] = last_word;
+  }
+  return TB_OK;
+}
+
+extern "C" tb_status tb_layout_describe(const tb_problem* pb, int32_t nbanks, tb_layout_info* info, int32_t* slot_of) {
+  if (!pb || !info || nbanks < 0) return TB_ERR_INVALID;
+  TnfLayoutOptions lo;
+  lo.nbanks = nbanks;
+  lo.lanes_per_set = 16;
+  lo.slot_align = nbanks > 0 ? nbanks : 4;
+  TnfLayout L;
+  std::string err;
+  tb_status rc = tb_build_layout(pb, lo, &L, &err);
+  if (rc != TB_OK) return rc;
+  *info = tb_layout_info();
+  info->nclasses = TBC_NUM;
+  info->nchunks = L.cls_begin[TBC_NUM];
+  info->nslots = L.nslots;
+  info->identity = L.identity ? 1 : 0;
+  for (int c = 0; c < TBC_NUM; ++c) {
+    const int n = L.cls_begin[c + 1] - L.cls_begin[c];
+    info->class_count[c] = n ? (n - 1) * 32 + L.cls_last[c] : 0;
+  }
+  info->loads_per_sweep = L.loads_per_sweep;
+  info->wavefronts_per_load = L.wavefronts_per_load;
+  if (slot_of) std::copy(L.slot_of.begin(), L.slot_of.end(), slot_of);
+  return TB_OK;
+}
+
+extern "C" const char* tb_layout_class_name(int32_t cls) { return tb_class_name(cls); }

@@ -2,20 +2,28 @@
 //
 // B200-native replacement of PIR::deduce / PIR::ask (called at reference
 // include/barebones_dive_and_solve.hpp:931,944,977; bodies live in lala-pc, not in the tree).
-// One thread evaluates one propagator on values it has already loaded into registers and returns
-// the candidate bounds; the caller publishes them with shared-memory atomicMax/atomicMin.
-// All candidates are computed from the *loaded* snapshot (Jacobi style); the greatest fixpoint is
-// schedule independent, so this agrees bit for bit with the sequential CPU oracle.
 //
-// Result flags: bit0 = a bound moved, bit1 = an interval is (or became) empty,
-//               bit2 = propagator not entailed on the loaded snapshot (fused `ask`).
+// The host layout pass (layout.cpp) sorts the propagator table into *classes* (tnf_classes.h): one
+// class = one operator + which operands are root constants + whether 32-bit arithmetic is exact.
+// A warp always evaluates 32 propagators of the same class, so the operator is a compile-time
+// constant here: no dispatch, no divergence, and operands that are constants cost no load.
+//
+// One thread evaluates one propagator on the bounds it loaded (Jacobi style: every candidate is
+// computed from the loaded snapshot) and publishes only the bounds that moved with shared-memory
+// atomicMax/atomicMin.  All rules are monotone and contracting, so the greatest fixpoint is schedule
+// independent and agrees bit for bit with the sequential CPU oracle.
+//
+// Failure detection: whoever publishes a bound that empties an interval *of its snapshot* flags
+// F_FAILED; an interval emptied by two threads that each saw a non-empty snapshot is seen empty by
+// the next chunk visit that loads it (bounds never move back), at the latest in the sweep that would
+// otherwise end the fixpoint.
 #pragma once
 #include <stdint.h>
 #include "../../include/turbo_b200.h"
+#include "tnf_classes.h"
 
 #define TBD_NINF INT32_MIN
 #define TBD_PINF INT32_MAX
-#define TB_OP_NOP 8            // padding propagator: never changes anything, always entailed
 
 #define F_CHANGED 1
 #define F_FAILED 2
@@ -24,6 +32,9 @@
 namespace tbd {
 
 struct Cand {          // candidate bounds for x, y, z (initialised to "no information")
+  int xl, xu, yl, yu, zl, zu;
+};
+struct Snap {          // the bounds one evaluation worked on (constants appear as singletons)
   int xl, xu, yl, yu, zl, zu;
 };
 
@@ -58,23 +69,12 @@ __device__ __forceinline__ long long max4(long long a, long long b, long long c,
   return max(max(a, b), max(c, d));
 }
 
-// ---- x = y + z ---------------------------------------------------------------------------------
-__device__ __forceinline__ void add(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
-  // Fast path: every bound in [-2^30, 2^30): plain 32-bit arithmetic cannot wrap and no infinity
-  // is involved. (v + 2^30) has its sign bit clear exactly for those values.
-  const unsigned B = 0x40000000u;
-  unsigned t = ((unsigned)xl + B) | ((unsigned)xu + B) | ((unsigned)yl + B) | ((unsigned)yu + B) |
-               ((unsigned)zl + B) | ((unsigned)zu + B);
-  if ((int)t >= 0) {
-    c.xl = yl + zl; c.xu = yu + zu;
-    c.yl = xl - zu; c.yu = xu - zl;
-    c.zl = xl - yu; c.zu = xu - yl;
-  } else {
-    long long exl = ext64(xl), exu = ext64(xu), eyl = ext64(yl), eyu = ext64(yu), ezl = ext64(zl), ezu = ext64(zu);
-    c.xl = clamp64(eyl + ezl); c.xu = clamp64(eyu + ezu);
-    c.yl = clamp64(exl - ezu); c.yu = clamp64(exu - ezl);
-    c.zl = clamp64(exl - eyu); c.zu = clamp64(exu - eyl);
-  }
+// ---- x = y + z on extended integers --------------------------------------------------------------
+__device__ __forceinline__ void add_ext(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
+  long long exl = ext64(xl), exu = ext64(xu), eyl = ext64(yl), eyu = ext64(yu), ezl = ext64(zl), ezu = ext64(zu);
+  c.xl = clamp64(eyl + ezl); c.xu = clamp64(eyu + ezu);
+  c.yl = clamp64(exl - ezu); c.yu = clamp64(exu - ezl);
+  c.zl = clamp64(exl - eyu); c.zu = clamp64(exu - eyl);
 }
 
 // quotient hull for  f = p / d  (d without 0, everything finite), rounded inward
@@ -84,7 +84,7 @@ __device__ __forceinline__ void quot(int pl, int pu, int dl, int du, int& ql, in
   qu = clamp64(max4(fdiv64(a, c), fdiv64(a, d), fdiv64(b, c), fdiv64(b, d)));
 }
 
-// ---- x = y * z ---------------------------------------------------------------------------------
+// ---- x = y * z -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mul(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
   if (fin(yl, yu) && fin(zl, zu)) {
     long long a = (long long)yl * zl, b = (long long)yl * zu, d = (long long)yu * zl, e = (long long)yu * zu;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void mul(int xl, int xu, int yl, int yu, int zl, int 
   }
 }
 
-// ---- x = y tdiv z, z != 0 ----------------------------------------------------------------------
+// ---- x = y tdiv z, z != 0 ----------------------------------------------------------------------------
 __device__ __forceinline__ void tdiv(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
   if (zl == 0) { c.zl = 1; zl = 1; }
   if (zu == 0) { c.zu = -1; zu = -1; }
@@ -145,7 +145,7 @@ __device__ __forceinline__ void tdiv(int xl, int xu, int yl, int yu, int zl, int
   }
 }
 
-// ---- x = y tmod z, z != 0 ----------------------------------------------------------------------
+// ---- x = y tmod z, z != 0 ----------------------------------------------------------------------------
 __device__ __forceinline__ void tmod(int xl, int xu, int yl, int yu, int zl, int zu, Cand& c) {
   (void)xl; (void)xu;
   if (zl == 0) { c.zl = 1; zl = 1; }
@@ -166,75 +166,135 @@ __device__ __forceinline__ void tmod(int xl, int xu, int yl, int yu, int zl, int
   c.xl = lo; c.xu = hi;
 }
 
-// The rare operators (MUL / TDIV / TMOD): kept out of line so that the hot loop stays small and
-// register-resident; candidates come back through one by-value struct.
-__device__ __noinline__ void rare_eval(int op, int xl, int xu, int yl, int yu, int zl, int zu, Cand* out) {
+// Operators whose arithmetic needs extended integers or 64 bits (ADD_G, MUL, TDIV, TMOD): out of
+// line, so that the specialised loops stay small; candidates come back through one struct.
+__device__ __noinline__ void wide_eval(int op, int xl, int xu, int yl, int yu, int zl, int zu, Cand* out) {
   Cand c;
   c.xl = TBD_NINF; c.xu = TBD_PINF; c.yl = TBD_NINF; c.yu = TBD_PINF; c.zl = TBD_NINF; c.zu = TBD_PINF;
-  if (op == TB_OP_MUL) mul(xl, xu, yl, yu, zl, zu, c);
+  if (op == TB_OP_ADD) add_ext(xl, xu, yl, yu, zl, zu, c);
+  else if (op == TB_OP_MUL) mul(xl, xu, yl, yu, zl, zu, c);
   else if (op == TB_OP_TDIV) tdiv(xl, xu, yl, yu, zl, zu, c);
   else tmod(xl, xu, yl, yu, zl, zu, c);
   *out = c;
 }
 
-// Hot operators, fully inlined. On entry n* hold the current bounds; on exit the narrowed ones
-// (new = current meet candidate). Returns whether the propagator is entailed on the snapshot.
-// `op` must be one of ADD, LEQ, EQ, MIN, MAX, NOP.
-__device__ __forceinline__ bool hot_eval(int op, int xl, int xu, int yl, int yu, int zl, int zu,
-                                         int& nxl, int& nxu, int& nyl, int& nyu, int& nzl, int& nzu) {
-  const bool ground = (xl == xu) & (yl == yu) & (zl == zu);
-  if (op == TB_OP_ADD) {
-    const unsigned B = 0x40000000u;
-    unsigned t = ((unsigned)xl + B) | ((unsigned)xu + B) | ((unsigned)yl + B) | ((unsigned)yu + B) |
-                 ((unsigned)zl + B) | ((unsigned)zu + B);
-    if ((int)t >= 0) {          // all bounds in [-2^30, 2^30): 32-bit arithmetic is exact, no infinity involved
-      nxl = max(xl, yl + zl); nxu = min(xu, yu + zu);
-      nyl = max(yl, xl - zu); nyu = min(yu, xu - zl);
-      nzl = max(zl, xl - yu); nzu = min(zu, xu - yl);
-    } else {
-      Cand c;
-      add(xl, xu, yl, yu, zl, zu, c);
-      nxl = max(xl, c.xl); nxu = min(xu, c.xu); nyl = max(yl, c.yl); nyu = min(yu, c.yu); nzl = max(zl, c.zl); nzu = min(zu, c.zu);
-    }
-    return ground;
-  }
-  if (op == TB_OP_LEQ) {
-    if (xl >= 1) { nyu = min(yu, zu); nzl = max(zl, yl); return yu <= zl; }
-    if (xu <= 0) { nyl = max(yl, succ(zl)); nzu = min(zu, pred(yu)); return yl > zu; }
-    if (yu <= zl) nxl = 1; else if (yl > zu) nxu = 0;
-    return false;
-  }
-  if (op == TB_OP_EQ) {
-    if (xl >= 1) {
-      nyl = max(yl, zl); nyu = min(yu, zu); nzl = nyl; nzu = nyu;
-      return (yl == yu) & (zl == zu) & (yl == zl);
-    }
-    if (xu <= 0) {
-      if (yl == yu && fin(yl, yu)) { if (zl == yl) nzl = yl + 1; if (zu == yl) nzu = yl - 1; }
-      if (zl == zu && fin(zl, zu)) { if (yl == zl) nyl = zl + 1; if (yu == zl) nyu = zl - 1; }
-      return (yu < zl) | (zu < yl);
-    }
-    if (yu < zl || zu < yl) nxu = 0;
-    else if (yl == yu && zl == zu && yl == zl) nxl = 1;
-    return false;
-  }
-  if (op == TB_OP_MIN) {
-    nxl = max(xl, min(yl, zl)); nxu = min(xu, min(yu, zu));
-    nyl = max(yl, xl); nzl = max(zl, xl);
-    if (yl > xu) nzu = min(zu, xu);
-    if (zl > xu) nyu = min(yu, xu);
-    return ground;
-  }
-  if (op == TB_OP_MAX) {
-    nxl = max(xl, max(yl, zl)); nxu = min(xu, max(yu, zu));
-    nyu = min(yu, xu); nzu = min(zu, xu);
-    if (yu < xl) nzl = max(zl, xl);
-    if (zu < xl) nyl = max(yl, xl);
-    return ground;
-  }
-  return true;   // TB_OP_NOP
+// ---- class traits ----------------------------------------------------------------------------------------
+// Which operands a class loads from the store; the others are constants carried in the propagator word
+// (…_XK / …_ZK) or implied by the class (…_T: x = 1, …_F: x = 0).
+__host__ __device__ constexpr bool cls_loads_x(int c) {
+  return !(c == TBC_ADD_XK || c == TBC_EQ_T || c == TBC_EQ_F || c == TBC_LEQ_T || c == TBC_LEQ_F);
+}
+__host__ __device__ constexpr bool cls_loads_z(int c) { return !(c == TBC_ADD_ZK || c == TBC_EQ_ZK || c == TBC_LEQ_ZK); }
+__host__ __device__ constexpr int cls_op(int c) {
+  return (c == TBC_ADD_S || c == TBC_ADD_XK || c == TBC_ADD_ZK || c == TBC_ADD_G) ? TB_OP_ADD
+       : c == TBC_MUL ? TB_OP_MUL : c == TBC_TDIV ? TB_OP_TDIV : c == TBC_TMOD ? TB_OP_TMOD
+       : c == TBC_MIN ? TB_OP_MIN : c == TBC_MAX ? TB_OP_MAX
+       : (c == TBC_EQ_S || c == TBC_EQ_T || c == TBC_EQ_F || c == TBC_EQ_ZK || c == TBC_EQ_G) ? TB_OP_EQ : TB_OP_LEQ;
+}
+// 32-bit arithmetic on the bounds is exact (every operand lives within +-2^29 at the root)
+__host__ __device__ constexpr bool cls_small(int c) {
+  return !(c == TBC_ADD_G || c == TBC_MUL || c == TBC_TDIV || c == TBC_TMOD || c == TBC_EQ_G || c == TBC_LEQ_G);
 }
 
-__device__ __forceinline__ bool is_rare(int op) { return op >= TB_OP_MUL && op <= TB_OP_TMOD; }
+// New bounds n* (already met with the snapshot s) of one propagator of class CLS.
+template <int CLS>
+__device__ __forceinline__ void narrow(const Snap& s, Snap& n) {
+  constexpr int op = cls_op(CLS);
+  const int xl = s.xl, xu = s.xu, yl = s.yl, yu = s.yu, zl = s.zl, zu = s.zu;
+  n = s;
+  if (CLS == TBC_ADD_G || op == TB_OP_MUL || op == TB_OP_TDIV || op == TB_OP_TMOD) {
+    Cand c;
+    wide_eval(op, xl, xu, yl, yu, zl, zu, &c);
+    n.xl = max(xl, c.xl); n.xu = min(xu, c.xu); n.yl = max(yl, c.yl); n.yu = min(yu, c.yu); n.zl = max(zl, c.zl); n.zu = min(zu, c.zu);
+  } else if (op == TB_OP_ADD) {
+    // max(a + b, c) / min(a + b, c) are single instructions on sm_100 (VIADDMNMX)
+    n.xl = __viaddmax_s32(yl, zl, xl); n.xu = __viaddmin_s32(yu, zu, xu);
+    n.yl = __viaddmax_s32(xl, -zu, yl); n.yu = __viaddmin_s32(xu, -zl, yu);
+    n.zl = __viaddmax_s32(xl, -yu, zl); n.zu = __viaddmin_s32(xu, -yl, zu);
+  } else if (op == TB_OP_MIN) {
+    n.xl = max(xl, min(yl, zl)); n.xu = min(xu, min(yu, zu));
+    n.yl = max(yl, xl); n.zl = max(zl, xl);
+    if (yl > xu) n.zu = min(zu, xu);
+    if (zl > xu) n.yu = min(yu, xu);
+  } else if (op == TB_OP_MAX) {
+    n.xl = max(xl, max(yl, zl)); n.xu = min(xu, max(yu, zu));
+    n.yu = min(yu, xu); n.zu = min(zu, xu);
+    if (yu < xl) n.zl = max(zl, xl);
+    if (zu < xl) n.yl = max(yl, xl);
+  } else if (op == TB_OP_LEQ) {
+    // The rules of the three cases (x true / x false / x undecided) are applied side by side: a rule of
+    // the "wrong" case only fires on stores the right case fails on too.
+    const bool t = xl >= 1, f = xu <= 0;
+    const int zl1 = cls_small(CLS) ? zl + 1 : succ(zl), yu1 = cls_small(CLS) ? yu - 1 : pred(yu);
+    if (t) { n.yu = min(yu, zu); n.zl = max(zl, yl); }
+    if (f) { n.yl = max(yl, zl1); n.zu = min(zu, yu1); }
+    if (yu <= zl) n.xl = max(xl, 1);
+    if (yl > zu) n.xu = min(xu, 0);
+  } else {   // TB_OP_EQ
+    const bool t = xl >= 1, f = xu <= 0;
+    if (t) { n.yl = max(yl, zl); n.yu = min(yu, zu); n.zl = n.yl; n.zu = n.yu; }
+    if (f) {
+      if (yl == yu && (cls_small(CLS) || fin(yl, yu))) { if (zl == yl) n.zl = yl + 1; if (zu == yl) n.zu = yl - 1; }
+      if (zl == zu && (cls_small(CLS) || fin(zl, zu))) { if (yl == zl) n.yl = zl + 1; if (yu == zl) n.yu = zl - 1; }
+    }
+    if (yu < zl || zu < yl) n.xu = min(xu, 0);
+    else if (yl == yu && zl == zu && yl == zl) n.xl = max(xl, 1);
+  }
+}
+
+// PIR::ask on a snapshot: is the propagator entailed?
+template <int CLS>
+__device__ __forceinline__ bool entailed(const Snap& s) {
+  constexpr int op = cls_op(CLS);
+  if (op == TB_OP_LEQ) return s.xl >= 1 ? s.yu <= s.zl : (s.xu <= 0 ? s.yl > s.zu : false);
+  if (op == TB_OP_EQ)
+    return s.xl >= 1 ? ((s.yl == s.yu) & (s.zl == s.zu) & (s.yl == s.zl)) : (s.xu <= 0 ? ((s.yu < s.zl) | (s.zu < s.yl)) : false);
+  return (s.xl == s.xu) & (s.yl == s.yu) & (s.zl == s.zu);
+}
+
+// One evaluation: load what the class loads, narrow, publish the bounds that moved.
+// a, b, c are the three fields of the propagator word (slots, or a constant for …K classes).
+// Sets `changed`; sets `failed` when a bound it publishes empties an interval of its snapshot (an interval
+// that was already empty when loaded is caught by `snapshot_empty` once per chunk visit). `s` keeps the
+// snapshot for that test and for the fused `ask`.
+template <int CLS, class Store>
+__device__ __forceinline__ void deduce(const Store& st, int a, int b, int c, Snap& s, unsigned& narrowed, bool& changed, bool& failed) {
+  constexpr bool LX = cls_loads_x(CLS), LZ = cls_loads_z(CLS);
+  if (LX) st.ld(a, s.xl, s.xu);
+  else if (CLS == TBC_ADD_XK) s.xl = s.xu = a;
+  else s.xl = s.xu = (CLS == TBC_EQ_T || CLS == TBC_LEQ_T) ? 1 : 0;
+  st.ld(b, s.yl, s.yu);
+  if (LZ) st.ld(c, s.zl, s.zu); else s.zl = s.zu = c;
+  Snap n;
+  narrow<CLS>(s, n);
+  changed = (n.yl != s.yl) | (n.yu != s.yu);
+  if (LX) changed |= (n.xl != s.xl) | (n.xu != s.xu);
+  if (LZ) changed |= (n.zl != s.zl) | (n.zu != s.zu);
+  failed = false;
+  if (changed) {
+    failed = n.yl > n.yu;
+    if (LX) {
+      failed |= n.xl > n.xu;
+      if (n.xl != s.xl) { st.tell_lb(a, n.xl); ++narrowed; }
+      if (n.xu != s.xu) { st.tell_ub(a, n.xu); ++narrowed; }
+    }
+    if (n.yl != s.yl) { st.tell_lb(b, n.yl); ++narrowed; }
+    if (n.yu != s.yu) { st.tell_ub(b, n.yu); ++narrowed; }
+    if (LZ) {
+      failed |= n.zl > n.zu;
+      if (n.zl != s.zl) { st.tell_lb(c, n.zl); ++narrowed; }
+      if (n.zu != s.zu) { st.tell_ub(c, n.zu); ++narrowed; }
+    }
+  }
+}
+
+// A loaded interval was already empty (two publishers that each saw a non-empty snapshot, or the caller).
+template <int CLS>
+__device__ __forceinline__ bool snapshot_empty(const Snap& s) {
+  bool e = s.yl > s.yu;
+  if (cls_loads_x(CLS)) e |= s.xl > s.xu;
+  if (cls_loads_z(CLS)) e |= s.zl > s.zu;
+  return e;
+}
 
 }  // namespace tbd

@@ -42,6 +42,9 @@ def lib():
         L.tb_import_peer_bounds.argtypes = [vp, vp, C.c_int32]
         L.tb_read_bound.argtypes = [vp, i32p]
         L.tb_get_config.argtypes = [vp, C.POINTER(abi.TbStats)]
+        L.tb_layout_describe.argtypes = [C.POINTER(abi.TbProblem), C.c_int32, C.POINTER(abi.TbLayoutInfo), i32p]
+        L.tb_layout_class_name.argtypes = [C.c_int32]
+        L.tb_layout_class_name.restype = C.c_char_p
         L.tb_destroy.argtypes = [vp]
         L.tb_destroy.restype = None
         L.tb_last_error.restype = C.c_char_p
@@ -62,6 +65,18 @@ def _check(rc):
 
 def _p(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+def layout_describe(problem, nbanks=16):
+    """The host layout pass on its own (no GPU): class histogram, variable placement, bank model."""
+    L = lib()
+    info = abi.TbLayoutInfo()
+    slot_of = np.zeros(max(1, problem.nvars), dtype=np.int32)
+    _check(L.tb_layout_describe(C.byref(problem.c), nbanks, C.byref(info), _p(slot_of)))
+    classes = {L.tb_layout_class_name(c).decode(): info.class_count[c] for c in range(info.nclasses)}
+    return dict(classes=classes, nchunks=info.nchunks, nslots=info.nslots, identity=bool(info.identity),
+                loads_per_sweep=info.loads_per_sweep, wavefronts_per_load=info.wavefronts_per_load,
+                slot_of=slot_of[:problem.nvars])
 
 
 def device_count():
