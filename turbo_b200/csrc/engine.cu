@@ -81,6 +81,12 @@ __device__ __forceinline__ void bulk_commit_wait_all() {
 // many bytes so that the mbarrier transaction count (20 bits) never overflows.
 #define BULK_CHUNK (128u * 1024u)
 
+// Threads per CTA: every thread evaluates TBC_U propagators per chunk visit, which takes up to 128 registers
+// for TBC_U = 2, so a CTA has at most 512 threads (1024 at 64 registers when TBC_U = 1).
+#ifndef TB_MAX_THREADS
+#define TB_MAX_THREADS (TBC_U >= 2 ? 512 : 1024)
+#endif
+
 // ================================================================================================
 // block context
 // ================================================================================================
@@ -115,11 +121,14 @@ struct StoreRef {           // STORE_SHARED / TCN_SHARED: shared memory of this 
   __device__ __forceinline__ void set(int v, int l, int u) const {
     asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr(v)), "r"(l), "r"(u) : "memory");
   }
-  __device__ __forceinline__ void tell_lb(int v, int n) const {
-    asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr(v)), "r"(n) : "memory");
+  // Publish a bound if it moved (n != old) and count it: three predicated instructions, no branch.
+  __device__ __forceinline__ void tell_lb(int v, int n, int old, unsigned& count) const {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, %3;\n\t@p red.shared.max.s32 [%1], %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                 : "+r"(count) : "r"(addr(v)), "r"(n), "r"(old) : "memory");
   }
-  __device__ __forceinline__ void tell_ub(int v, int n) const {
-    asm volatile("red.shared.min.s32 [%0+4], %1;" ::"r"(addr(v)), "r"(n) : "memory");
+  __device__ __forceinline__ void tell_ub(int v, int n, int old, unsigned& count) const {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, %3;\n\t@p red.shared.min.s32 [%1+4], %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                 : "+r"(count) : "r"(addr(v)), "r"(n), "r"(old) : "memory");
   }
   // VStore::embed (barebones :707,761-764,805,846,853): in-place meet, returns "changed"
   __device__ __forceinline__ bool embed(int v, int l, int u) const {
@@ -139,8 +148,8 @@ struct StoreRef<TB_MEM_GLOBAL> {   // L2-resident global memory (ld.cg: never th
   __device__ __forceinline__ void set(int v, int l, int u) const {
     asm volatile("st.global.cg.v2.s32 [%0], {%1, %2};" ::"l"(p + v), "r"(l), "r"(u) : "memory");
   }
-  __device__ __forceinline__ void tell_lb(int v, int n) const { atomicMax(&p[v].x, n); }
-  __device__ __forceinline__ void tell_ub(int v, int n) const { atomicMin(&p[v].y, n); }
+  __device__ __forceinline__ void tell_lb(int v, int n, int old, unsigned& count) const { if (n != old) { atomicMax(&p[v].x, n); ++count; } }
+  __device__ __forceinline__ void tell_ub(int v, int n, int old, unsigned& count) const { if (n != old) { atomicMin(&p[v].y, n); ++count; } }
   __device__ __forceinline__ bool embed(int v, int l, int u) const {
     int ol = atomicMax(&p[v].x, l), ou = atomicMin(&p[v].y, u);
     return l > ol || u < ou;
@@ -166,11 +175,11 @@ struct StoreRef<TB_MEM_STORE_CLUSTER> {
   __device__ __forceinline__ void set(int v, int l, int u) const {
     asm volatile("st.shared::cluster.v2.s32 [%0], {%1, %2};" ::"r"(addr(v)), "r"(l), "r"(u) : "memory");
   }
-  __device__ __forceinline__ void tell_lb(int v, int n) const {
-    asm volatile("red.shared::cluster.max.s32 [%0], %1;" ::"r"(addr(v)), "r"(n) : "memory");
+  __device__ __forceinline__ void tell_lb(int v, int n, int old, unsigned& count) const {
+    if (n != old) { asm volatile("red.shared::cluster.max.s32 [%0], %1;" ::"r"(addr(v)), "r"(n) : "memory"); ++count; }
   }
-  __device__ __forceinline__ void tell_ub(int v, int n) const {
-    asm volatile("red.shared::cluster.min.s32 [%0], %1;" ::"r"(addr(v) + 4u), "r"(n) : "memory");
+  __device__ __forceinline__ void tell_ub(int v, int n, int old, unsigned& count) const {
+    if (n != old) { asm volatile("red.shared::cluster.min.s32 [%0], %1;" ::"r"(addr(v) + 4u), "r"(n) : "memory"); ++count; }
   }
   __device__ __forceinline__ bool embed(int v, int l, int u) const {
     const unsigned a = addr(v);
@@ -284,74 +293,112 @@ struct Ctx {
   // (`warp_fixpoint`, :951-962) the warp iterates the chunk to a warp-local fixpoint before moving on.
   // `changed` / `failed` are warp-uniform; `notent` is per lane: the fused `ask` (:972-982) evaluated on the
   // last snapshot, which in the sweep where nothing changed is the final store.
+  // One lane's TBC_U words of a chunk (adjacent in the table: one vector load).
+  struct Words { unsigned long long w[TBC_U]; };
+
   struct Walk {
     int ch;                 // current chunk of this warp
-    int widx;               // index of this lane's word in the warp's NEXT chunk
-    unsigned long long cur; // this lane's word of the current chunk
-    unsigned evals;         // warp evaluations (x32 propagators) of this sweep
-    unsigned late_chg;      // chunk visits that ended on a change (AC1: every changing visit)
+    int widx;               // index of this lane's first word in the warp's NEXT chunk
+    Words cur;              // this lane's words of the current chunk
+    unsigned evals;         // warp evaluations (x 32 TBC_U propagators) of this sweep
     unsigned pad_evals;     // propagator evaluations spent on padding lanes
+    int late_chg;           // a chunk visit ended on a change (AC1: some visit changed something)
     int failed;             // warp-uniform
-    int notent;             // per lane: some propagator of this lane is not entailed
+    int notent;             // per lane: non-zero iff some propagator of this lane is not entailed
   };
 
-  // Next chunk's word. The global table is followed by 32 chunks of padding, so the prefetch needs no bound
+  // Next chunk's words. The global table is followed by 32 chunks of padding, so the prefetch needs no bound
   // check; the shared copy (TCN_SHARED) is not, and clamps.
-  __device__ __forceinline__ unsigned long long load_word(int i) const {
-    if (MEM == TB_MEM_TCN_SHARED) return words[min(i, P.nchunks * 32 - 1)];
-    return __ldg(words + i);
+  __device__ __forceinline__ Words load_words(int i) const {
+    Words r;
+    if (MEM == TB_MEM_TCN_SHARED) i = min(i, (P.nchunks * 32 - 1) * TBC_U);
+    if (TBC_U == 2) {
+      const ulonglong2 t = MEM == TB_MEM_TCN_SHARED ? *(const ulonglong2*)(words + i) : __ldg((const ulonglong2*)(words + i));
+      r.w[0] = t.x; r.w[TBC_U - 1] = t.y;
+    } else {
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) r.w[u] = MEM == TB_MEM_TCN_SHARED ? words[i + u] : __ldg(words + i + u);
+    }
+    return r;
   }
 
+  // Orders this thread's published bounds before its re-reads (see tbd::emptied).
+  __device__ __forceinline__ void publish_fence() const {
+    if (MEM == TB_MEM_STORE_CLUSTER) asm volatile("fence.sc.cluster;" ::: "memory");
+    else asm volatile("fence.sc.cta;" ::: "memory");
+  }
+
+  // The part of one sweep that falls in class CLS. A warp walks the whole table ch = warp, warp + nwarps, ...
+  // (so the classes load-balance together and the next chunk's words are always prefetched, across class
+  // boundaries too); the table is sorted by class, so the walk is a chain of per-class loops in each of which
+  // the operator is a compile-time constant. A chunk is 32 * TBC_U propagators of one class. With WAC1
+  // (`warp_fixpoint`, :951-962) the warp iterates the chunk to a warp-local fixpoint before moving on.
+  // Every branch below is warp-uniform (votes), so the hot path carries no reconvergence bookkeeping.
   template <int CLS>
   __device__ __forceinline__ void sweep_class(Walk& w, const bool wac1, const int nwarps) {
     const int ce = P.cls_begin[CLS + 1];
-    if (w.ch >= ce) return;
-    unsigned e0;
+    unsigned e0 = w.evals;
+    bool dead = false;
     do {
-      const unsigned long long nxt = load_word(w.widx);
-      int fa, fb, fc;
-      decode_word<CLS>(w.cur, fa, fb, fc);
-      tbd::Snap s;
+      const Words nxt = load_words(w.widx);
+      int fa[TBC_U], fb[TBC_U], fc[TBC_U];
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) decode_word<CLS>(w.cur.w[u], fa[u], fb[u], fc[u]);
+      tbd::Snap s[TBC_U];
       e0 = w.evals;
-      bool wchg, wfail;
-      do {
-        bool chg, fail;
-        tbd::deduce<CLS>(store, fa, fb, fc, s, narrowed, chg, fail);
-        wchg = __any_sync(0xffffffffu, chg); wfail = __any_sync(0xffffffffu, fail);
+      for (;;) {
+        tbd::Snap n[TBC_U];
+        bool chg = false;
+#pragma unroll
+        for (int u = 0; u < TBC_U; ++u) tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
+#pragma unroll
+        for (int u = 0; u < TBC_U; ++u) { tbd::narrow<CLS>(s[u], n[u]); chg |= tbd::snap_changed<CLS>(s[u], n[u]); }
         ++w.evals;
-      } while (wac1 & wchg & !wfail);
-      if (wchg) ++w.late_chg;
-      if (!tbd::entailed<CLS>(s)) w.notent = 1;
-      if (wfail | __any_sync(0xffffffffu, tbd::snapshot_empty<CLS>(s))) { w.failed = 1; return; }
+        if (!__any_sync(0xffffffffu, chg)) break;          // the chunk is at its warp-local fixpoint
+        // somebody narrowed something: publish (per bound, predicated), then look for emptied intervals
+#pragma unroll
+        for (int u = 0; u < TBC_U; ++u) tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], n[u], narrowed);
+        publish_fence();
+        bool fail = false;
+#pragma unroll
+        for (int u = 0; u < TBC_U; ++u) fail |= tbd::emptied<CLS>(store, fa[u], fb[u], fc[u]);
+        dead = __any_sync(0xffffffffu, fail);
+        if (dead | !wac1) { w.late_chg = 1; break; }
+      }
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) w.notent |= tbd::not_entailed_bits<CLS>(s[u]);
       w.ch += nwarps;
-      w.widx += nwarps * 32;
+      w.widx += nwarps * 32 * TBC_U;
       w.cur = nxt;
-    } while (w.ch < ce);
+    } while (w.ch < ce && !dead);
+    if (dead) w.failed = 1;
     // the class's last chunk is padded with copies of its last propagator: do not count those lanes
-    if (w.ch - nwarps == ce - 1) w.pad_evals += (w.evals - e0) * (unsigned)(32 - P.cls_last[CLS]);
+    if (w.ch - nwarps == ce - 1) w.pad_evals += (w.evals - e0) * (unsigned)(32 * TBC_U - P.cls_last[CLS]);
   }
 
   // Returns the OR of the flag bits of the last sweep; `iters` = number of block sweeps.
   __device__ int fixpoint(int& iters) {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the walk's loop control
+    // lives in uniform registers and its branches need no reconvergence bookkeeping)
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = T >> 5;
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
     int it = 0, f;
     for (;; ++it) {
       Walk w;
-      w.ch = warp; w.evals = w.late_chg = w.pad_evals = 0; w.failed = 0; w.notent = 0;
-      w.widx = warp * 32 + lane;
-      w.cur = load_word(w.widx);
-      w.widx += nwarps * 32;
-#define TB_SWEEP(CLS) if (!w.failed) sweep_class<CLS>(w, wac1, nwarps);
+      w.ch = warp; w.evals = w.pad_evals = 0; w.late_chg = 0; w.failed = 0; w.notent = 0;
+      w.widx = (warp * 32 + lane) * TBC_U;
+      w.cur = load_words(w.widx);
+      w.widx += nwarps * 32 * TBC_U;
+#define TB_SWEEP(CLS) if (w.ch < P.cls_begin[CLS + 1] && !w.failed) sweep_class<CLS>(w, wac1, nwarps);
       TB_SWEEP(TBC_ADD_S) TB_SWEEP(TBC_ADD_XK) TB_SWEEP(TBC_ADD_ZK) TB_SWEEP(TBC_ADD_G)
       TB_SWEEP(TBC_MUL) TB_SWEEP(TBC_TDIV) TB_SWEEP(TBC_TMOD) TB_SWEEP(TBC_MIN) TB_SWEEP(TBC_MAX)
       TB_SWEEP(TBC_EQ_S) TB_SWEEP(TBC_EQ_T) TB_SWEEP(TBC_EQ_F) TB_SWEEP(TBC_EQ_ZK) TB_SWEEP(TBC_EQ_G)
       TB_SWEEP(TBC_LEQ_S) TB_SWEEP(TBC_LEQ_T) TB_SWEEP(TBC_LEQ_F) TB_SWEEP(TBC_LEQ_ZK) TB_SWEEP(TBC_LEQ_G)
 #undef TB_SWEEP
-      deductions += (unsigned long long)w.evals * 32ull - (unsigned long long)w.pad_evals;
+      deductions += (unsigned long long)w.evals * (unsigned long long)(32 * TBC_U) - (unsigned long long)w.pad_evals;
       // a visit changed something iff it took more than one evaluation (WAC1) or ended on a change
-      const unsigned visits = (unsigned)(w.ch - warp) / (unsigned)nwarps + (w.failed ? 1u : 0u);
-      const bool changed = w.evals + w.late_chg > visits;
+      const unsigned visits = (unsigned)(w.ch - warp) / (unsigned)nwarps;
+      const bool changed = w.evals > visits || w.late_chg;
       int bits = (changed ? F_CHANGED : 0) | (w.failed ? F_FAILED : 0) | (w.notent ? F_NOT_ENTAILED : 0);
       bits = __reduce_or_sync(0xffffffffu, bits);
       const int slot = it % 3;
@@ -657,7 +704,7 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM>& k, Ctl* local, unsigned char*
   if (MEM == TB_MEM_TCN_SHARED) {
     // stage the propagator table once: TMA bulk copy global -> shared
     unsigned char* sprops = dyn + store_bytes;
-    const unsigned bytes = (unsigned)((size_t)P.nchunks * 32 * 8);
+    const unsigned bytes = (unsigned)((size_t)P.nchunks * 32 * TBC_U * 8);
     if (threadIdx.x == 0 && bytes) {
       fence_proxy_async();
       mbar_expect_tx(&local->mbar, bytes);
@@ -687,7 +734,7 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM>& k) {
 
 // The persistent dive-and-solve kernel (gpu_barebones_solve, barebones :620-901).
 template <int MEM>
-__global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ DevParams P) {
+__global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_constant__ DevParams P) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
@@ -729,7 +776,7 @@ __global__ void __launch_bounds__(1024) solve_kernel(const __grid_constant__ Dev
 
 // One fixpoint per block on caller-provided stores (tb_propagate / tb_propagate_batch).
 template <int MEM>
-__global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__ DevParams P, int nstores,
+__global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_constant__ DevParams P, int nstores,
                                                          const int* in_lb, const int* in_ub,
                                                          int* out_lb, int* out_ub, int* out_failed, int repeat) {
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -747,14 +794,13 @@ __global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__
       if (tid == 0) c.leaf = 0;
       k.sync();
       int empty_seen = 0;
-      for (int sl = tid; sl < P.vpad; sl += T) {
-        const int v = P.var_of[sl];
-        int l = 0, u = 0;
-        if (v >= 0) {
-          l = in_lb[(size_t)s * P.nvars + v]; u = in_ub[(size_t)s * P.nvars + v];
-          empty_seen |= (l > u) & (int)P.referenced[v];
-        }
-        k.store.set(sl, l, u);
+      if (P.vpad != P.nvars) {                 // padding slots hold the singleton 0
+        for (int sl = tid; sl < P.vpad; sl += T) if (P.var_of[sl] < 0) k.store.set(sl, 0, 0);
+      }
+      for (int v = tid; v < P.nvars; v += T) {
+        const int l = in_lb[(size_t)s * P.nvars + v], u = in_ub[(size_t)s * P.nvars + v];
+        empty_seen |= (l > u) & (int)P.referenced[v];
+        k.store.set(P.slot_of[v], l, u);
       }
       if (empty_seen) atomicOr(&c.leaf, 1);
       k.sync();
@@ -777,7 +823,7 @@ __global__ void __launch_bounds__(1024) propagate_kernel(const __grid_constant__
 
 // EPS dive only (tb_dive / tb_dive_batch).
 template <int MEM>
-__global__ void __launch_bounds__(1024) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
+__global__ void __launch_bounds__(TB_MAX_THREADS) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
                                                     int depth, int* out_lb, int* out_ub, int* out_remaining, int* out_kind) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
@@ -902,7 +948,7 @@ static int env_int(const char* name, int dflt) {
 // The sweep assigns chunk ch to warp (ch mod nwarps) with a mask: the warp count is a power of two.
 static int pow2_threads(int t) {
   int p = 32;
-  while (p * 2 <= std::min(t, 1024)) p *= 2;
+  while (p * 2 <= std::min(t, TB_MAX_THREADS)) p *= 2;
   return p;
 }
 
@@ -953,7 +999,7 @@ static tb_status configure(tb_solver* s) {
     s->store_bytes = (size_t)s->P.vpad * 8;
     s->mem_kind = kind;
     s->shared_bytes = (size_t)s->P.vc * 8;
-    s->threads = s->opt.threads_per_block > 0 ? pow2_threads(s->opt.threads_per_block) : 1024;
+    s->threads = s->opt.threads_per_block > 0 ? pow2_threads(s->opt.threads_per_block) : TB_MAX_THREADS;
     s->blocks_per_sm = 1;
     // how many clusters can be co-resident is asked from the driver once the kernel attributes are set
     s->num_blocks = std::max(1, s->num_sms / cluster);
@@ -967,8 +1013,9 @@ static tb_status configure(tb_solver* s) {
   if (threads <= 0) {
     bps = std::min(bps, 8);
     threads = bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024);
+    threads = std::min(threads, TB_MAX_THREADS);
     // do not use more threads than there is work per sweep
-    while (threads > 128 && threads / 2 >= s->P.nchunks * 32) threads /= 2;
+    while (threads > 128 && threads / 2 >= s->P.nchunks * 32) threads /= 2;   // at least one chunk per warp
   }
   threads = pow2_threads(threads);
   bps = std::max(1, std::min(bps, 2048 / threads));
@@ -1009,6 +1056,17 @@ static tb_status set_smem_attr(tb_solver* s) {
       int workers = nclusters;
       if (s->opt.or_blocks > 0) workers = std::min(workers, s->opt.or_blocks);
       s->num_blocks = std::max(1, workers);
+    } else {
+      // registers limit the resident CTAs too: ask the driver what really fits (persistent kernel: one wave)
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<m>, s->threads, s->shared_bytes));
+      if (per_sm < 1) { set_error("the solve kernel does not fit on an SM with this configuration"); return TB_ERR_UNSUPPORTED; }
+      if (per_sm < s->blocks_per_sm) {
+        s->blocks_per_sm = per_sm;
+        int blocks = per_sm * s->num_sms;
+        if (s->opt.or_blocks > 0) blocks = std::min(blocks, s->opt.or_blocks);
+        s->num_blocks = std::max(1, blocks);
+      }
     }
     return TB_OK;
   });
@@ -1086,9 +1144,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     int per_class[TBC_NUM] = {0};
     for (int i = 0; i < pb->nprops; ++i) { bool sw; ++per_class[tb_classify(pb->props[i], pb->lb, pb->ub, &sw)]; }
     int nchunks = 0;
-    for (int c = 0; c < TBC_NUM; ++c) nchunks += (per_class[c] + 31) / 32;
+    for (int c = 0; c < TBC_NUM; ++c) nchunks += (per_class[c] + 32 * TBC_U - 1) / (32 * TBC_U);
     P.nchunks = nchunks;
-    s->prop_bytes = (size_t)nchunks * 32 * 8;
+    s->prop_bytes = (size_t)nchunks * 32 * TBC_U * 8;
     s->store_bytes = (size_t)std::max(32, (pb->nvars + 31) / 32 * 32) * 8;     // shared placements pad to the 32 banks
   }
   if ((rc = configure(s)) != TB_OK) return fail(rc);
@@ -1124,8 +1182,8 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     const TnfLayout& L = s->layout;
     unsigned long long* d = nullptr;
     // 32 chunks of padding behind the table: a warp prefetches its next chunk without a bound check
-    if ((rc = dev_alloc(s, &d, L.words.size() + 32 * 32))) return fail(rc);
-    if (cudaMemset(d, 0, (L.words.size() + 32 * 32) * 8) != cudaSuccess ||
+    if ((rc = dev_alloc(s, &d, L.words.size() + 32 * 32 * TBC_U))) return fail(rc);
+    if (cudaMemset(d, 0, (L.words.size() + 32 * 32 * TBC_U) * 8) != cudaSuccess ||
         (L.words.size() && cudaMemcpy(d, L.words.data(), L.words.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
     P.words = d;
     std::vector<int> var_of((size_t)P.vpad, -1);

@@ -88,21 +88,23 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
 
-  // chunk table: indices into `items`, -1 = padding (filled with a copy of the class's last propagator)
+  // row table: rows of 32 lanes holding indices into `items`, -1 = padding (filled with a copy of the class's
+  // last propagator). A chunk is TBC_U consecutive rows of one class: lane l of a warp evaluates lane l of each.
+  const int CH = 32 * TBC_U;
   std::vector<int> lanes;
-  lanes.reserve((size_t)P + 32 * TBC_NUM);
+  lanes.reserve((size_t)P + (size_t)CH * TBC_NUM);
   {
     size_t i = 0;
     for (int c = 0; c < TBC_NUM; ++c) {
-      L.cls_begin[c] = (int)(lanes.size() / 32);
+      L.cls_begin[c] = (int)(lanes.size() / CH);
       size_t n = 0;
       while (i < order.size() && items[order[i]].cls == c) { lanes.push_back(order[i]); ++i; ++n; }
-      L.cls_last[c] = n ? (int)((n - 1) % 32 + 1) : 0;
-      while (lanes.size() % 32) lanes.push_back(-1);
+      L.cls_last[c] = n ? (int)((n - 1) % CH + 1) : 0;
+      while (lanes.size() % CH) lanes.push_back(-1);
     }
-    L.cls_begin[TBC_NUM] = (int)(lanes.size() / 32);
+    L.cls_begin[TBC_NUM] = (int)(lanes.size() / CH);
   }
-  const int nchunks = L.cls_begin[TBC_NUM];
+  const int nrows = (int)(lanes.size() / 32);
 
   // ---- variable placement --------------------------------------------------------------------------------
   L.slot_of.resize((size_t)V);
@@ -110,18 +112,21 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
   L.identity = true;
   // role sets: for every chunk and every loaded operand position, the distinct variables the 32 lanes read
   std::vector<std::vector<int>> sets;
-  if (nchunks) sets.reserve((size_t)nchunks * 6);
+  if (nrows) sets.reserve((size_t)nrows * 6);
   // (a 64-bit shared-memory load is served one half-warp at a time: lanes_per_set = 16)
   const int LPS = opt.lanes_per_set > 0 ? opt.lanes_per_set : 32;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int cls = items[lanes[(size_t)ch * 32]].cls;
+  for (int row = 0; row < nrows; ++row) {
+    int first = -1, real = 0;
+    for (int l = 0; l < 32; ++l) if (lanes[(size_t)row * 32 + l] >= 0) { if (first < 0) first = lanes[(size_t)row * 32 + l]; ++real; }
+    if (first < 0) continue;                      // a row of padding only
+    const int cls = items[first].cls;
     for (int role = 0; role < 3; ++role) {
       if ((role == 0 && !loads_x(cls)) || (role == 2 && !loads_z(cls))) continue;
-      L.loads_per_sweep += (uint64_t)(ch + 1 == L.cls_begin[cls + 1] ? L.cls_last[cls] : 32);
+      L.loads_per_sweep += (uint64_t)real;
       for (int l0 = 0; l0 < 32; l0 += LPS) {
         std::vector<int> vs;
         for (int l = l0; l < l0 + LPS; ++l) {
-          const int id = lanes[(size_t)ch * 32 + l];
+          const int id = lanes[(size_t)row * 32 + l];
           if (id < 0) continue;
           const Item& it = items[id];
           vs.push_back(role == 0 ? it.x : (role == 1 ? it.y : it.z));
@@ -196,10 +201,13 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
   }
 
   // ---- device words ------------------------------------------------------------------------------------------
+  // lane l of chunk ch reads its TBC_U words (one per row) with one vector load: they are adjacent
   L.words.assign(lanes.size(), 0);
   uint64_t last_word = 0;
   for (size_t i = 0; i < lanes.size(); ++i) {
-    if (lanes[i] < 0) { L.words[i] = last_word; continue; }
+    const size_t row = i / 32, lane = i % 32, ch = row / TBC_U, u = row % TBC_U;
+    const size_t dst = (ch * 32 + lane) * TBC_U + u;
+    if (lanes[i] < 0) { L.words[dst] = last_word; continue; }
     const Item& it = items[lanes[i]];
     uint64_t f0, f1, f2;
     if (loads_x(it.cls)) f0 = (uint64_t)L.slot_of[it.x];
@@ -209,7 +217,7 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
     if (loads_z(it.cls)) f2 = (uint64_t)L.slot_of[it.z];
     else f2 = (uint64_t)((uint32_t)pb->lb[it.z] & TBC_FIELD_MASK);
     last_word = f0 | (f1 << TBC_FIELD_BITS) | (f2 << (2 * TBC_FIELD_BITS));
-    L.words[i] = last_word;
+    L.words[dst] = last_word;
   }
   return TB_OK;
 }
@@ -231,7 +239,7 @@ extern "C" tb_status tb_layout_describe(const tb_problem* pb, int32_t nbanks, tb
   info->identity = L.identity ? 1 : 0;
   for (int c = 0; c < TBC_NUM; ++c) {
     const int n = L.cls_begin[c + 1] - L.cls_begin[c];
-    info->class_count[c] = n ? (n - 1) * 32 + L.cls_last[c] : 0;
+    info->class_count[c] = n ? (n - 1) * 32 * TBC_U + L.cls_last[c] : 0;
   }
   info->loads_per_sweep = L.loads_per_sweep;
   info->wavefronts_per_load = L.wavefronts_per_load;

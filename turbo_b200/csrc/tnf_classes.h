@@ -31,6 +31,12 @@ enum {
   TBC_NUM
 };
 
+// Propagators per thread and chunk visit: a chunk is 32 * TBC_U propagators of one class (TBC_U "rows" of 32);
+// lane l evaluates lane l of every row. Two rows per visit halve the per-visit and per-vote overhead.
+#ifndef TBC_U
+#define TBC_U 2
+#endif
+
 #define TBC_FIELD_BITS 21
 #define TBC_FIELD_MASK 0x1FFFFFu
 #define TBC_MAX_VARS (1 << TBC_FIELD_BITS)

@@ -13,10 +13,7 @@
 // atomicMax/atomicMin.  All rules are monotone and contracting, so the greatest fixpoint is schedule
 // independent and agrees bit for bit with the sequential CPU oracle.
 //
-// Failure detection: whoever publishes a bound that empties an interval *of its snapshot* flags
-// F_FAILED; an interval emptied by two threads that each saw a non-empty snapshot is seen empty by
-// the next chunk visit that loads it (bounds never move back), at the latest in the sweep that would
-// otherwise end the fixpoint.
+// Failure detection is on the publishing side (see `emptied`).
 #pragma once
 #include <stdint.h>
 #include "../../include/turbo_b200.h"
@@ -252,49 +249,59 @@ __device__ __forceinline__ bool entailed(const Snap& s) {
   return (s.xl == s.xu) & (s.yl == s.yu) & (s.zl == s.zu);
 }
 
-// One evaluation: load what the class loads, narrow, publish the bounds that moved.
+// One evaluation = three phases, so that a thread can interleave the phases of several propagators.
 // a, b, c are the three fields of the propagator word (slots, or a constant for …K classes).
-// Sets `changed`; sets `failed` when a bound it publishes empties an interval of its snapshot (an interval
-// that was already empty when loaded is caught by `snapshot_empty` once per chunk visit). `s` keeps the
-// snapshot for that test and for the fused `ask`.
 template <int CLS, class Store>
-__device__ __forceinline__ void deduce(const Store& st, int a, int b, int c, Snap& s, unsigned& narrowed, bool& changed, bool& failed) {
-  constexpr bool LX = cls_loads_x(CLS), LZ = cls_loads_z(CLS);
-  if (LX) st.ld(a, s.xl, s.xu);
+__device__ __forceinline__ void load_snap(const Store& st, int a, int b, int c, Snap& s) {
+  if (cls_loads_x(CLS)) st.ld(a, s.xl, s.xu);
   else if (CLS == TBC_ADD_XK) s.xl = s.xu = a;
   else s.xl = s.xu = (CLS == TBC_EQ_T || CLS == TBC_LEQ_T) ? 1 : 0;
   st.ld(b, s.yl, s.yu);
-  if (LZ) st.ld(c, s.zl, s.zu); else s.zl = s.zu = c;
-  Snap n;
-  narrow<CLS>(s, n);
-  changed = (n.yl != s.yl) | (n.yu != s.yu);
-  if (LX) changed |= (n.xl != s.xl) | (n.xu != s.xu);
-  if (LZ) changed |= (n.zl != s.zl) | (n.zu != s.zu);
-  failed = false;
-  if (changed) {
-    failed = n.yl > n.yu;
-    if (LX) {
-      failed |= n.xl > n.xu;
-      if (n.xl != s.xl) { st.tell_lb(a, n.xl); ++narrowed; }
-      if (n.xu != s.xu) { st.tell_ub(a, n.xu); ++narrowed; }
-    }
-    if (n.yl != s.yl) { st.tell_lb(b, n.yl); ++narrowed; }
-    if (n.yu != s.yu) { st.tell_ub(b, n.yu); ++narrowed; }
-    if (LZ) {
-      failed |= n.zl > n.zu;
-      if (n.zl != s.zl) { st.tell_lb(c, n.zl); ++narrowed; }
-      if (n.zu != s.zu) { st.tell_ub(c, n.zu); ++narrowed; }
-    }
+  if (cls_loads_z(CLS)) st.ld(c, s.zl, s.zu); else s.zl = s.zu = c;
+}
+template <int CLS>
+__device__ __forceinline__ bool snap_changed(const Snap& s, const Snap& n) {
+  bool changed = (n.yl != s.yl) | (n.yu != s.yu);
+  if (cls_loads_x(CLS)) changed |= (n.xl != s.xl) | (n.xu != s.xu);
+  if (cls_loads_z(CLS)) changed |= (n.zl != s.zl) | (n.zu != s.zu);
+  return changed;
+}
+// Publish the bounds that moved (lanes whose propagator changed nothing publish nothing).
+template <int CLS, class Store>
+__device__ __forceinline__ void publish(const Store& st, int a, int b, int c, const Snap& s, const Snap& n, unsigned& narrowed) {
+  if (cls_loads_x(CLS)) {
+    st.tell_lb(a, n.xl, s.xl, narrowed);
+    st.tell_ub(a, n.xu, s.xu, narrowed);
+  }
+  st.tell_lb(b, n.yl, s.yl, narrowed);
+  st.tell_ub(b, n.yu, s.yu, narrowed);
+  if (cls_loads_z(CLS)) {
+    st.tell_lb(c, n.zl, s.zl, narrowed);
+    st.tell_ub(c, n.zu, s.zu, narrowed);
   }
 }
 
-// A loaded interval was already empty (two publishers that each saw a non-empty snapshot, or the caller).
-template <int CLS>
-__device__ __forceinline__ bool snapshot_empty(const Snap& s) {
-  bool e = s.yl > s.yu;
-  if (cls_loads_x(CLS)) e |= s.xl > s.xu;
-  if (cls_loads_z(CLS)) e |= s.zl > s.zu;
+// Failure detection, on the publishing side only: after its updates (and a fence) a publisher re-reads the
+// intervals it touched; an interval is empty for it if its own update emptied it, or if a concurrent
+// publisher's update did and became visible first. Two publishers that empty an interval together (one
+// raises lb, the other lowers ub, each from a non-empty snapshot) are ordered by their fences, so at least one
+// of them sees both updates. Intervals nobody publishes to cannot become empty.
+template <int CLS, class Store>
+__device__ __forceinline__ bool emptied(const Store& st, int a, int b, int c) {
+  int l, u;
+  st.ld(b, l, u);
+  bool e = l > u;
+  if (cls_loads_x(CLS)) { st.ld(a, l, u); e |= l > u; }
+  if (cls_loads_z(CLS)) { st.ld(c, l, u); e |= l > u; }
   return e;
+}
+
+// Non-zero iff the propagator is not entailed on the snapshot (the fused `ask`).
+template <int CLS>
+__device__ __forceinline__ int not_entailed_bits(const Snap& s) {
+  constexpr int op = cls_op(CLS);
+  if (op == TB_OP_LEQ || op == TB_OP_EQ) return entailed<CLS>(s) ? 0 : 1;
+  return (s.xl ^ s.xu) | (s.yl ^ s.yu) | (s.zl ^ s.zu);
 }
 
 }  // namespace tbd
