@@ -298,8 +298,8 @@ struct Ctx {
 
   struct Walk {
     int ch;                 // current chunk of this warp
-    int widx;               // index of this lane's first word in the warp's NEXT chunk
-    Words cur;              // this lane's words of the current chunk
+    int widx;               // index of this lane's first word in the chunk the warp visits after the next one
+    Words cur, nxt;         // this lane's words of the current chunk and of the next one (in flight)
     unsigned evals;         // warp evaluations (x 32 TBC_U propagators) of this sweep
     unsigned pad_evals;     // propagator evaluations spent on padding lanes
     int late_chg;           // a chunk visit ended on a change (AC1: some visit changed something)
@@ -307,8 +307,8 @@ struct Ctx {
     int notent;             // per lane: non-zero iff some propagator of this lane is not entailed
   };
 
-  // Next chunk's words. The global table is followed by 32 chunks of padding, so the prefetch needs no bound
-  // check; the shared copy (TCN_SHARED) is not, and clamps.
+  // A chunk's words are requested at the end of the visit before the previous one. The global table is followed
+  // by 64 chunks of padding, so the prefetch needs no bound check; the shared copy (TCN_SHARED) is not, and clamps.
   __device__ __forceinline__ Words load_words(int i) const {
     Words r;
     if (MEM == TB_MEM_TCN_SHARED) i = min(i, (P.nchunks * 32 - 1) * TBC_U);
@@ -340,24 +340,27 @@ struct Ctx {
     unsigned e0 = w.evals;
     bool dead = false;
     do {
-      const Words nxt = load_words(w.widx);
       int fa[TBC_U], fb[TBC_U], fc[TBC_U];
 #pragma unroll
       for (int u = 0; u < TBC_U; ++u) decode_word<CLS>(w.cur.w[u], fa[u], fb[u], fc[u]);
       tbd::Snap s[TBC_U];
       e0 = w.evals;
       for (;;) {
-        tbd::Snap n[TBC_U];
         bool chg = false;
 #pragma unroll
         for (int u = 0; u < TBC_U; ++u) tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
 #pragma unroll
-        for (int u = 0; u < TBC_U; ++u) { tbd::narrow<CLS>(s[u], n[u]); chg |= tbd::snap_changed<CLS>(s[u], n[u]); }
+        for (int u = 0; u < TBC_U; ++u) chg |= tbd::would_change<CLS>(s[u]);
         ++w.evals;
         if (!__any_sync(0xffffffffu, chg)) break;          // the chunk is at its warp-local fixpoint
-        // somebody narrowed something: publish (per bound, predicated), then look for emptied intervals
+        // somebody narrows something: compute the new bounds, publish the ones that moved (per bound,
+        // predicated), then look for emptied intervals
 #pragma unroll
-        for (int u = 0; u < TBC_U; ++u) tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], n[u], narrowed);
+        for (int u = 0; u < TBC_U; ++u) {
+          tbd::Snap n;
+          tbd::narrow<CLS>(s[u], n);
+          tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], n, narrowed);
+        }
         publish_fence();
         bool fail = false;
 #pragma unroll
@@ -368,8 +371,13 @@ struct Ctx {
 #pragma unroll
       for (int u = 0; u < TBC_U; ++u) w.notent |= tbd::not_entailed_bits<CLS>(s[u]);
       w.ch += nwarps;
+      // Rotate the prefetch queue: `nxt` was requested a whole visit ago, and the new request lands directly in
+      // `nxt` (a register copy of data still in flight would wait for the whole L2 round trip). The guard is
+      // always true; it ties the copy to a value produced at the end of the visit, otherwise the scheduler
+      // moves the copy to the top of the visit, right behind the request it depends on.
+      if (w.evals != 0u) w.cur = w.nxt;
+      w.nxt = load_words(w.widx);
       w.widx += nwarps * 32 * TBC_U;
-      w.cur = nxt;
     } while (w.ch < ce && !dead);
     if (dead) w.failed = 1;
     // the class's last chunk is padded with copies of its last propagator: do not count those lanes
@@ -388,6 +396,8 @@ struct Ctx {
       w.ch = warp; w.evals = w.pad_evals = 0; w.late_chg = 0; w.failed = 0; w.notent = 0;
       w.widx = (warp * 32 + lane) * TBC_U;
       w.cur = load_words(w.widx);
+      w.widx += nwarps * 32 * TBC_U;
+      w.nxt = load_words(w.widx);
       w.widx += nwarps * 32 * TBC_U;
 #define TB_SWEEP(CLS) if (w.ch < P.cls_begin[CLS + 1] && !w.failed) sweep_class<CLS>(w, wac1, nwarps);
       TB_SWEEP(TBC_ADD_S) TB_SWEEP(TBC_ADD_XK) TB_SWEEP(TBC_ADD_ZK) TB_SWEEP(TBC_ADD_G)
@@ -1181,9 +1191,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   {
     const TnfLayout& L = s->layout;
     unsigned long long* d = nullptr;
-    // 32 chunks of padding behind the table: a warp prefetches its next chunk without a bound check
-    if ((rc = dev_alloc(s, &d, L.words.size() + 32 * 32 * TBC_U))) return fail(rc);
-    if (cudaMemset(d, 0, (L.words.size() + 32 * 32 * TBC_U) * 8) != cudaSuccess ||
+    // 64 chunks of padding behind the table: a warp prefetches two visits ahead without a bound check
+    if ((rc = dev_alloc(s, &d, L.words.size() + 64 * 32 * TBC_U))) return fail(rc);
+    if (cudaMemset(d, 0, (L.words.size() + 64 * 32 * TBC_U) * 8) != cudaSuccess ||
         (L.words.size() && cudaMemcpy(d, L.words.data(), L.words.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
     P.words = d;
     std::vector<int> var_of((size_t)P.vpad, -1);

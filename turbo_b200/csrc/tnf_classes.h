@@ -12,13 +12,13 @@
 #pragma once
 
 enum {
-  TBC_ADD_S = 0,   // x = y + z, every operand within +-2^29 at the root
+  TBC_ADD_S = 0,   // x = y + z, every operand within +-2^28 at the root
   TBC_ADD_XK,      // k = y + z
   TBC_ADD_ZK,      // x = y + k
   TBC_ADD_G,       // x = y + z on extended integers (infinite or huge bounds)
   TBC_MUL, TBC_TDIV, TBC_TMOD,
   TBC_MIN, TBC_MAX,
-  TBC_EQ_S,        // x = (y == z), y and z within +-2^29
+  TBC_EQ_S,        // x = (y == z), y and z within +-2^28
   TBC_EQ_T,        // y == z          (x is the constant 1)
   TBC_EQ_F,        // y != z          (x is the constant 0)
   TBC_EQ_ZK,       // x = (y == k)
@@ -41,4 +41,4 @@ enum {
 #define TBC_FIELD_MASK 0x1FFFFFu
 #define TBC_MAX_VARS (1 << TBC_FIELD_BITS)
 #define TBC_CONST_LIMIT (1 << (TBC_FIELD_BITS - 1))     // constants in [-2^20, 2^20) fit a field
-#define TBC_SMALL_LIMIT (1 << 29)                       // "small": every bound within [-2^29, 2^29]
+#define TBC_SMALL_LIMIT (1 << 28)                       // "small": every bound within [-2^28, 2^28]: sums of three fit 32 bits

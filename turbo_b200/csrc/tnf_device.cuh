@@ -188,7 +188,7 @@ __host__ __device__ constexpr int cls_op(int c) {
        : c == TBC_MIN ? TB_OP_MIN : c == TBC_MAX ? TB_OP_MAX
        : (c == TBC_EQ_S || c == TBC_EQ_T || c == TBC_EQ_F || c == TBC_EQ_ZK || c == TBC_EQ_G) ? TB_OP_EQ : TB_OP_LEQ;
 }
-// 32-bit arithmetic on the bounds is exact (every operand lives within +-2^29 at the root)
+// 32-bit arithmetic on the bounds is exact (every operand lives within +-2^28 at the root)
 __host__ __device__ constexpr bool cls_small(int c) {
   return !(c == TBC_ADD_G || c == TBC_MUL || c == TBC_TDIV || c == TBC_TMOD || c == TBC_EQ_G || c == TBC_LEQ_G);
 }
@@ -266,6 +266,33 @@ __device__ __forceinline__ bool snap_changed(const Snap& s, const Snap& n) {
   if (cls_loads_z(CLS)) changed |= (n.zl != s.zl) | (n.zu != s.zu);
   return changed;
 }
+// Would `narrow` move a bound of a loaded operand?  This is what every evaluation computes; the new bounds
+// themselves are only computed when some lane of the warp answers yes.  For the additions the six tests
+// "candidate beyond current bound" are six 3-input adds whose maximum is positive iff something moves, which
+// is about half the ALU work of min/max + compare (the ALU pipe is the throughput limit of this loop).
+template <int CLS>
+__device__ __forceinline__ bool would_change(const Snap& s) {
+  if (CLS == TBC_ADD_S) {
+    const int d1 = s.yl + s.zl - s.xl, d2 = s.xu - s.yu - s.zu;
+    const int d3 = s.xl - s.zu - s.yl, d4 = s.yu - s.xu + s.zl;
+    const int d5 = s.xl - s.yu - s.zl, d6 = s.zu - s.xu + s.yl;
+    return max(__vimax3_s32(d1, d2, d3), __vimax3_s32(d4, d5, d6)) > 0;
+  }
+  if (CLS == TBC_ADD_XK) {      // x is the constant s.xl
+    const int d3 = s.xl - s.zu - s.yl, d4 = s.yu - s.xl + s.zl;
+    const int d5 = s.xl - s.yu - s.zl, d6 = s.zu - s.xl + s.yl;
+    return max(__vimax3_s32(d3, d4, d5), d6) > 0;
+  }
+  if (CLS == TBC_ADD_ZK) {      // z is the constant s.zl
+    const int d1 = s.yl + s.zl - s.xl, d2 = s.xu - s.yu - s.zl;
+    const int d3 = s.xl - s.zl - s.yl, d4 = s.yu - s.xu + s.zl;
+    return max(__vimax3_s32(d1, d2, d3), d4) > 0;
+  }
+  Snap n;
+  narrow<CLS>(s, n);
+  return snap_changed<CLS>(s, n);
+}
+
 // Publish the bounds that moved (lanes whose propagator changed nothing publish nothing).
 template <int CLS, class Store>
 __device__ __forceinline__ void publish(const Store& st, int a, int b, int c, const Snap& s, const Snap& n, unsigned& narrowed) {
