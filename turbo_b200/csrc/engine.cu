@@ -247,7 +247,7 @@ struct Ctx {
   // ---- copies between the block store and a global image of it ---------------------------------
   // An image is P.vpad * 8 bytes; with a cluster it is C slices of vc * 8 bytes, one per CTA, and every
   // CTA moves its own slice with its own mbarrier.
-  __device__ void load_store(const int* gsrc) {
+  __device__ __forceinline__ void load_store(const int* gsrc) {
     sync();
     if (MEM == TB_MEM_GLOBAL) {
       const unsigned bytes = (unsigned)P.vpad * 8u;
@@ -268,7 +268,7 @@ struct Ctx {
       if (MEM == TB_MEM_STORE_CLUSTER) sync();     // every slice has landed before anybody gathers from it
     }
   }
-  __device__ void save_store(int* gdst) {
+  __device__ __forceinline__ void save_store(int* gdst) {
     sync();
     if (MEM == TB_MEM_GLOBAL) {
       const unsigned bytes = (unsigned)P.vpad * 8u;
@@ -296,6 +296,15 @@ struct Ctx {
   // One lane's TBC_U words of a chunk (adjacent in the table: one vector load).
   struct Words { unsigned long long w[TBC_U]; };
 
+  // What the sweeps touch, copied out of the context into registers for the duration of one fixpoint: the
+  // context itself lives in local memory whenever a kernel calls the fixpoint from more than one place, and the
+  // volatile accesses of the loop would otherwise re-read its fields from there at every evaluation.
+  struct Hot {
+    StoreRef<MEM> store;
+    const unsigned long long* words;
+    unsigned narrowed;
+  };
+
   struct Walk {
     int ch;                 // current chunk of this warp
     int widx;               // index of this lane's first word in the chunk the warp visits after the next one
@@ -309,7 +318,7 @@ struct Ctx {
 
   // A chunk's words are requested at the end of the visit before the previous one. The global table is followed
   // by 64 chunks of padding, so the prefetch needs no bound check; the shared copy (TCN_SHARED) is not, and clamps.
-  __device__ __forceinline__ Words load_words(int i) const {
+  __device__ __forceinline__ Words load_words(const unsigned long long* words, int i) const {
     Words r;
     if (MEM == TB_MEM_TCN_SHARED) i = min(i, (P.nchunks * 32 - 1) * TBC_U);
     if (TBC_U == 2) {
@@ -335,7 +344,9 @@ struct Ctx {
   // (`warp_fixpoint`, :951-962) the warp iterates the chunk to a warp-local fixpoint before moving on.
   // Every branch below is warp-uniform (votes), so the hot path carries no reconvergence bookkeeping.
   template <int CLS>
-  __device__ __forceinline__ void sweep_class(Walk& w, const bool wac1, const int nwarps) {
+  __device__ __forceinline__ void sweep_class(Hot& h, Walk& w, const bool wac1, const int nwarps) {
+    const StoreRef<MEM>& store = h.store;
+    unsigned& narrowed = h.narrowed;
     const int ce = P.cls_begin[CLS + 1];
     unsigned e0 = w.evals;
     bool dead = false;
@@ -350,18 +361,17 @@ struct Ctx {
 #pragma unroll
         for (int u = 0; u < TBC_U; ++u) tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
 #pragma unroll
-        for (int u = 0; u < TBC_U; ++u) chg |= tbd::would_change<CLS>(s[u]);
+        for (int u = 0; u < TBC_U; ++u) chg |= tbd::has_work<CLS>(s[u]);
         ++w.evals;
         if (!__any_sync(0xffffffffu, chg)) break;          // the chunk is at its warp-local fixpoint
-        // somebody narrows something: compute the new bounds, publish the ones that moved (per bound,
-        // predicated), then look for emptied intervals
+        // somebody has work: compute the new bounds, publish the ones that moved (per bound, predicated),
+        // then re-read and look for empty intervals
 #pragma unroll
         for (int u = 0; u < TBC_U; ++u) {
           tbd::Snap n;
           tbd::narrow<CLS>(s[u], n);
           tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], n, narrowed);
         }
-        publish_fence();
         bool fail = false;
 #pragma unroll
         for (int u = 0; u < TBC_U; ++u) fail |= tbd::emptied<CLS>(store, fa[u], fb[u], fc[u]);
@@ -376,7 +386,7 @@ struct Ctx {
       // always true; it ties the copy to a value produced at the end of the visit, otherwise the scheduler
       // moves the copy to the top of the visit, right behind the request it depends on.
       if (w.evals != 0u) w.cur = w.nxt;
-      w.nxt = load_words(w.widx);
+      w.nxt = load_words(h.words, w.widx);
       w.widx += nwarps * 32 * TBC_U;
     } while (w.ch < ce && !dead);
     if (dead) w.failed = 1;
@@ -385,27 +395,30 @@ struct Ctx {
   }
 
   // Returns the OR of the flag bits of the last sweep; `iters` = number of block sweeps.
-  __device__ int fixpoint(int& iters) {
+  __device__ __forceinline__ int fixpoint(int& iters) {
     // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so the walk's loop control
     // lives in uniform registers and its branches need no reconvergence bookkeeping)
     const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = T >> 5;
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
+    Hot h;
+    h.store = store; h.words = words; h.narrowed = narrowed;
+    unsigned long long ded = 0;
     int it = 0, f;
     for (;; ++it) {
       Walk w;
       w.ch = warp; w.evals = w.pad_evals = 0; w.late_chg = 0; w.failed = 0; w.notent = 0;
       w.widx = (warp * 32 + lane) * TBC_U;
-      w.cur = load_words(w.widx);
+      w.cur = load_words(h.words, w.widx);
       w.widx += nwarps * 32 * TBC_U;
-      w.nxt = load_words(w.widx);
+      w.nxt = load_words(h.words, w.widx);
       w.widx += nwarps * 32 * TBC_U;
-#define TB_SWEEP(CLS) if (w.ch < P.cls_begin[CLS + 1] && !w.failed) sweep_class<CLS>(w, wac1, nwarps);
+#define TB_SWEEP(CLS) if (w.ch < P.cls_begin[CLS + 1] && !w.failed) sweep_class<CLS>(h, w, wac1, nwarps);
       TB_SWEEP(TBC_ADD_S) TB_SWEEP(TBC_ADD_XK) TB_SWEEP(TBC_ADD_ZK) TB_SWEEP(TBC_ADD_G)
       TB_SWEEP(TBC_MUL) TB_SWEEP(TBC_TDIV) TB_SWEEP(TBC_TMOD) TB_SWEEP(TBC_MIN) TB_SWEEP(TBC_MAX)
       TB_SWEEP(TBC_EQ_S) TB_SWEEP(TBC_EQ_T) TB_SWEEP(TBC_EQ_F) TB_SWEEP(TBC_EQ_ZK) TB_SWEEP(TBC_EQ_G)
       TB_SWEEP(TBC_LEQ_S) TB_SWEEP(TBC_LEQ_T) TB_SWEEP(TBC_LEQ_F) TB_SWEEP(TBC_LEQ_ZK) TB_SWEEP(TBC_LEQ_G)
 #undef TB_SWEEP
-      deductions += (unsigned long long)w.evals * (unsigned long long)(32 * TBC_U) - (unsigned long long)w.pad_evals;
+      ded += (unsigned long long)w.evals * (unsigned long long)(32 * TBC_U) - (unsigned long long)w.pad_evals;
       // a visit changed something iff it took more than one evaluation (WAC1) or ended on a change
       const unsigned visits = (unsigned)(w.ch - warp) / (unsigned)nwarps;
       const bool changed = w.evals > visits || w.late_chg;
@@ -419,6 +432,8 @@ struct Ctx {
       if (!(f & F_CHANGED) || (f & F_FAILED)) break;
     }
     iters = it + 1;
+    narrowed = h.narrowed;
+    deductions += ded;
     // leave slot 0 clean for the next call (nobody reads flags until the next fixpoint's barrier)
     sync();
     if (tid < 3) c.flags[tid] = 0;
@@ -429,7 +444,7 @@ struct Ctx {
   // ---- propagate() (barebones :903-1031) -----------------------------------------------------------
   // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
   // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
-  __device__ void propagate() {
+  __device__ __forceinline__ void propagate() {
     unsigned long long t0 = 0;
     if (tid == 0) t0 = globaltimer_ns();
     int iters = 0, f;
@@ -499,7 +514,7 @@ struct Ctx {
   }
 
   // thread 0 only
-  __device__ void push_decision(int val_order, int var) {
+  __device__ __forceinline__ void push_decision(int val_order, int var) {
     if (c.depth >= P.max_depth) { st->error = TB_ERR_DEPTH; st->exhaustive = 0; c.stop = 1; *P.stop = 1; c.pushed = 0; return; }
     int l, u; store.ld(var, l, u);
     Decision d;
@@ -520,7 +535,7 @@ struct Ctx {
   }
 
   // Returns (uniformly) whether a decision was pushed at dec[depth-1].
-  __device__ bool split() {
+  __device__ __forceinline__ bool split() {
     const int lane = tid & 31;
     for (;;) {
       const int s = c.cur_strategy;       // uniform (barrier before every read)
@@ -567,7 +582,7 @@ struct Ctx {
 
   // ---- EPS dive (barebones :663-741) ------------------------------------------------------------------
   // Dives from the problem root following the bits of `idx`. Returns remaining depth (uniform).
-  __device__ int dive(unsigned long long idx, int depth_power) {
+  __device__ __forceinline__ int dive(unsigned long long idx, int depth_power) {
     
     if (tid == 0) {
       c.cur_strategy = 0; c.next_unassigned = 0; c.depth = 0;
@@ -599,66 +614,143 @@ struct Ctx {
     return c.remaining_depth;
   }
 
-  // ---- solve one subproblem (barebones :742-871) -----------------------------------------------------
-  __device__ void solve_subproblem() {
-    
-    if (tid == 0 && P.has_eps_strategy) { c.cur_strategy = max(1, c.cur_strategy); c.next_unassigned = 0; }
-    sync();
-    while (!c.stop) {
-      // I. inject the incumbent bound (thread 0), detect an unconstrained objective
-      if (tid == 0 && P.obj_var >= 0) {
-        int appx = *(volatile int*)P.appx_best_bound;
-        if (appx != TBD_PINF) {
-          store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
-          store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
-        }
-        if (appx == TBD_NINF) { c.stop = 1; *P.stop = 1; }
-      }
-      sync();
-      if (c.stop) break;
-      // II. propagate
-      propagate();
-      // III. branch
-      if (!c.leaf) {
-        if (c.depth == 0) {
-          save_store(g_root);
-          if (tid == 0) { c.snap_strategy = c.cur_strategy; c.snap_next_unassigned = c.next_unassigned; }
-          sync();
-        }
-        bool pushed = split();
+  // ---- the whole search of one worker (barebones :656-886) -----------------------------------------------
+  // Main loop B-G of gpu_barebones_solve: take a subproblem, dive to it (steps C-D, :663-714), skip its
+  // subtree if the dive hit a leaf (E, :718-741), otherwise solve it by depth-first branch and bound with
+  // restore-from-root + decision replay (F, :742-871), then ask the dispenser for the next one (G, :873-885).
+  // Written as one flat state machine around a SINGLE propagate() call: with one call site the whole node
+  // step is inlined, the context stays in registers and the kernel parameters stay in the constant bank
+  // (two call sites cost ~25 % of the node rate: the fixpoint went out of line and re-read both from memory).
+  __device__ __forceinline__ void search() {
+    enum { M_START, M_DIVE, M_SOLVE, M_SOLVE_END, M_NEXT };
+    const unsigned long long nsub = P.num_subproblems;
+    const unsigned long long world = (unsigned long long)P.world, rank = (unsigned long long)P.rank;
+    unsigned long long idx = 0;
+    int mode = M_START;
+    for (;;) {
+      if (mode == M_START) {
+        idx = c.subproblem_k * world + rank;     // this GPU's shard: idx = rank (mod world)
+        if (idx >= nsub || c.stop) break;
+        sync();
         if (tid == 0) {
-          if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
-          else {
-            Decision& d = dec[c.depth - 1];
-            d.cur = 0;
-            store.embed(d.var, d.clb0, d.cub0);
+          c.cur_strategy = 0; c.next_unassigned = 0; c.depth = 0;
+          c.remaining_depth = P.subproblems_power; c.leaf = 0; c.failed = 0;
+          c.t_mark = (long long)globaltimer_ns();
+        }
+        load_store(P.root_store);
+        sync();
+        mode = M_DIVE;
+      }
+      if (mode == M_DIVE && !(c.remaining_depth > 0 && !c.leaf && !c.stop)) {
+        // the dive is over: at the subproblem (remaining depth 0), or at a leaf above it
+        if (tid == 0) st->t_dive += (long long)globaltimer_ns() - c.t_mark;
+        sync();
+        const int remaining = c.remaining_depth;
+        if (c.leaf && !c.stop) {
+          // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
+          if (tid == 0) {
+            unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
+            unsigned long long next_k = next <= rank ? 0ull : (next - rank + world - 1ull) / world;
+            atomicMax(P.next_subproblem, next_k);
+            if ((idx & ((1ull << remaining) - 1ull)) == 0ull) st->eps_skipped += next - idx;
+          }
+          mode = M_NEXT;
+        } else if (!c.stop) {
+          if (tid == 0 && P.has_eps_strategy) { c.cur_strategy = max(1, c.cur_strategy); c.next_unassigned = 0; }
+          sync();
+          mode = M_SOLVE;
+        } else mode = M_NEXT;
+      }
+      if (mode == M_SOLVE) {
+        if (c.stop) mode = M_SOLVE_END;
+        else {
+          // I. inject the incumbent bound (thread 0), detect an unconstrained objective
+          if (tid == 0 && P.obj_var >= 0) {
+            int appx = *(volatile int*)P.appx_best_bound;
+            if (appx != TBD_PINF) {
+              store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
+              store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
+            }
+            if (appx == TBD_NINF) { c.stop = 1; *P.stop = 1; }
+          }
+          sync();
+          if (c.stop) mode = M_SOLVE_END;
+        }
+      }
+      if (mode == M_SOLVE_END) {
+        sync();
+        if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->eps_solved += 1;
+        mode = M_NEXT;
+      }
+      if (mode == M_NEXT) {
+        sync();
+        if (tid == 0 && !c.stop) c.subproblem_k = atomicAdd(P.next_subproblem, 1ull);
+        sync();
+        mode = M_START;
+        continue;
+      }
+
+      // II. one node
+      if (mode == M_DIVE) sync();
+      propagate();
+
+      if (mode == M_DIVE) {
+        if (!c.leaf) {
+          bool pushed = split();
+          if (tid == 0) {
+            if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
+            else {
+              --c.remaining_depth;
+              --c.depth;                        // decisions are not recorded while diving
+              const Decision& d = dec[0];
+              int bit = (int)((idx >> c.remaining_depth) & 1ull);
+              store.embed(d.var, bit ? d.clb1 : d.clb0, bit ? d.cub1 : d.cub0);
+            }
           }
         }
         sync();
-      }
-      // IV. backtrack: follow the rope, restore from the subproblem root, replay the decisions
-      if (c.leaf) {
-        if (c.depth == 0) break;
-        sync();
-        if (tid == 0) { const Decision& d = dec[c.depth - 1]; c.depth = d.cur == 0 ? d.rope0 : d.rope1; }
-        sync();
-        const int depth = c.depth;
-        if (depth == -1) break;
-        load_store(g_root);
-        for (int i = tid; i < depth - 1; i += T) {
-          const Decision d = dec[i];
-          store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+      } else {
+        // III. branch
+        if (!c.leaf) {
+          if (c.depth == 0) {
+            save_store(g_root);
+            if (tid == 0) { c.snap_strategy = c.cur_strategy; c.snap_next_unassigned = c.next_unassigned; }
+            sync();
+          }
+          bool pushed = split();
+          if (tid == 0) {
+            if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
+            else {
+              Decision& d = dec[c.depth - 1];
+              d.cur = 0;
+              store.embed(d.var, d.clb0, d.cub0);
+            }
+          }
+          sync();
         }
-        if (tid == 0) {
-          Decision& d = dec[depth - 1];
-          d.cur += 1;
-          store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
-          c.cur_strategy = c.snap_strategy; c.next_unassigned = c.snap_next_unassigned;
+        // IV. backtrack: follow the rope, restore from the subproblem root, replay the decisions
+        if (c.leaf) {
+          if (c.depth == 0) { mode = M_SOLVE_END; continue; }
+          sync();
+          if (tid == 0) { const Decision& d = dec[c.depth - 1]; c.depth = d.cur == 0 ? d.rope0 : d.rope1; }
+          sync();
+          const int depth = c.depth;
+          if (depth == -1) { mode = M_SOLVE_END; continue; }
+          load_store(g_root);
+          for (int i = tid; i < depth - 1; i += T) {
+            const Decision d = dec[i];
+            store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+          }
+          if (tid == 0) {
+            Decision& d = dec[depth - 1];
+            d.cur += 1;
+            store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+            c.cur_strategy = c.snap_strategy; c.next_unassigned = c.snap_next_unassigned;
+          }
+          sync();
         }
-        sync();
       }
     }
-    sync();
   }
 };
 
@@ -754,29 +846,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
   BlockStats* st = k.st;
   if (tid == 0) c.subproblem_k = (unsigned long long)k.slot;
   k.sync();
-  const unsigned long long nsub = P.num_subproblems;
-  const unsigned long long world = (unsigned long long)P.world, rank = (unsigned long long)P.rank;
-  for (;;) {
-    const unsigned long long idx = c.subproblem_k * world + rank;   // this GPU's shard: idx ≡ rank (mod world)
-    if (idx >= nsub || c.stop) break;
-    k.sync();
-    const int remaining = k.dive(idx, P.subproblems_power);
-    if (c.leaf && !c.stop) {
-      // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
-      if (tid == 0) {
-        unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
-        unsigned long long next_k = next <= rank ? 0ull : (next - rank + world - 1ull) / world;
-        atomicMax(P.next_subproblem, next_k);
-        if ((idx & ((1ull << remaining) - 1ull)) == 0ull) st->eps_skipped += next - idx;
-      }
-    } else if (!c.stop) {
-      k.solve_subproblem();
-      if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->eps_solved += 1;
-    }
-    k.sync();
-    if (tid == 0 && !c.stop) c.subproblem_k = atomicAdd(P.next_subproblem, 1ull);
-    k.sync();
-  }
+  k.search();
   if (tid == 0) {
     if (!(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->blocks_done = 1;
     st->t_idle = (long long)(globaltimer_ns() - P.t_start);

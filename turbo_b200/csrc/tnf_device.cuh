@@ -13,7 +13,7 @@
 // atomicMax/atomicMin.  All rules are monotone and contracting, so the greatest fixpoint is schedule
 // independent and agrees bit for bit with the sequential CPU oracle.
 //
-// Failure detection is on the publishing side (see `emptied`).
+// Failure detection: see `emptied`.
 #pragma once
 #include <stdint.h>
 #include "../../include/turbo_b200.h"
@@ -266,12 +266,23 @@ __device__ __forceinline__ bool snap_changed(const Snap& s, const Snap& n) {
   if (cls_loads_z(CLS)) changed |= (n.zl != s.zl) | (n.zu != s.zu);
   return changed;
 }
-// Would `narrow` move a bound of a loaded operand?  This is what every evaluation computes; the new bounds
-// themselves are only computed when some lane of the warp answers yes.  For the additions the six tests
-// "candidate beyond current bound" are six 3-input adds whose maximum is positive iff something moves, which
-// is about half the ALU work of min/max + compare (the ALU pipe is the throughput limit of this loop).
+// A loaded interval is empty.
 template <int CLS>
-__device__ __forceinline__ bool would_change(const Snap& s) {
+__device__ __forceinline__ bool snapshot_empty(const Snap& s) {
+  bool e = s.yl > s.yu;
+  if (cls_loads_x(CLS)) e |= s.xl > s.xu;
+  if (cls_loads_z(CLS)) e |= s.zl > s.zu;
+  return e;
+}
+
+// "This evaluation has something to do": `narrow` would move a bound of a loaded operand, or a loaded interval
+// is empty. This is what every evaluation computes; the new bounds themselves are only computed when some lane
+// of the warp answers yes. For the additions the six tests "candidate beyond current bound" are six 3-input
+// adds whose maximum is positive iff something moves, about half the ALU work of min/max + compare; for the
+// three-variable addition that maximum is also positive whenever an operand is empty (if none of the six
+// candidates improves a bound then yl + zl <= xl <= yl + zu, ... which forces xl <= xu, yl <= yu, zl <= zu).
+template <int CLS>
+__device__ __forceinline__ bool has_work(const Snap& s) {
   if (CLS == TBC_ADD_S) {
     const int d1 = s.yl + s.zl - s.xl, d2 = s.xu - s.yu - s.zu;
     const int d3 = s.xl - s.zu - s.yl, d4 = s.yu - s.xu + s.zl;
@@ -281,16 +292,16 @@ __device__ __forceinline__ bool would_change(const Snap& s) {
   if (CLS == TBC_ADD_XK) {      // x is the constant s.xl
     const int d3 = s.xl - s.zu - s.yl, d4 = s.yu - s.xl + s.zl;
     const int d5 = s.xl - s.yu - s.zl, d6 = s.zu - s.xl + s.yl;
-    return max(__vimax3_s32(d3, d4, d5), d6) > 0;
+    return (max(__vimax3_s32(d3, d4, d5), d6) > 0) | snapshot_empty<CLS>(s);
   }
   if (CLS == TBC_ADD_ZK) {      // z is the constant s.zl
     const int d1 = s.yl + s.zl - s.xl, d2 = s.xu - s.yu - s.zl;
     const int d3 = s.xl - s.zl - s.yl, d4 = s.yu - s.xu + s.zl;
-    return max(__vimax3_s32(d1, d2, d3), d4) > 0;
+    return (max(__vimax3_s32(d1, d2, d3), d4) > 0) | snapshot_empty<CLS>(s);
   }
   Snap n;
   narrow<CLS>(s, n);
-  return snap_changed<CLS>(s, n);
+  return snap_changed<CLS>(s, n) | snapshot_empty<CLS>(s);
 }
 
 // Publish the bounds that moved (lanes whose propagator changed nothing publish nothing).
@@ -308,11 +319,11 @@ __device__ __forceinline__ void publish(const Store& st, int a, int b, int c, co
   }
 }
 
-// Failure detection, on the publishing side only: after its updates (and a fence) a publisher re-reads the
-// intervals it touched; an interval is empty for it if its own update emptied it, or if a concurrent
-// publisher's update did and became visible first. Two publishers that empty an interval together (one
-// raises lb, the other lowers ub, each from a non-empty snapshot) are ordered by their fences, so at least one
-// of them sees both updates. Intervals nobody publishes to cannot become empty.
+// Failure detection: an empty interval gives every propagator that loads it "work" (has_work), and whoever has
+// work re-reads the intervals it loads after publishing and reports the empty ones. So an interval emptied by
+// this thread's own update is reported at once, and one emptied by two publishers together (one raises lb, the
+// other lowers ub, each from a non-empty snapshot) at the latest by the next evaluation that loads it: no
+// sweep can end without change while a loaded interval is empty.
 template <int CLS, class Store>
 __device__ __forceinline__ bool emptied(const Store& st, int a, int b, int c) {
   int l, u;
