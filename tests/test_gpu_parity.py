@@ -239,3 +239,69 @@ def test_cluster_dive_and_solve(eng, orc):
         o = orc.solve(pb, depth=3)
         for key in ("nodes", "fails", "solutions", "eps_solved_subproblems", "eps_skipped_subproblems", "depth_max"):
             assert g["stats"][key] == o["stats"][key], (seed, key)
+
+
+# ---- the layout pass specialises the device table on the root domains -------------------------------------
+
+def test_propagate_rejects_a_store_outside_the_root(eng):
+    pb = tnf_gen.planted(50, 80, 1)
+    lb, ub = pb.lb.copy(), pb.ub.copy()
+    v = int(np.argmax(pb.ub - pb.lb))
+    ub[v] += 1
+    with eng.Solver(pb) as s:
+        with pytest.raises(eng.TurboError) as e:
+            s.propagate(lb, ub)
+        assert "root store" in str(e.value)
+        s.propagate(pb.lb, pb.ub)           # the solver is still usable
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_caller_store_with_an_empty_folded_constant(eng, orc, kind):
+    """Variable 1 is the constant 1 and the `x` of a LEQ: the device table folds it away (class leq_t) and
+    never loads it, yet a caller store in which it is empty must fail like the oracle's deduce does; an
+    empty variable no propagator mentions must not."""
+    lb = [0, 1, 2, 0, 0, 7]
+    ub = [0, 1, 2, 9, 9, 7]
+    props = np.array([(abi.OP_LEQ, 1, 3, 4), (abi.OP_ADD, 4, 3, 2)], np.int32)
+    pb = abi.Problem(lb, ub, props)
+    for bad, want_failed in ((1, True), (5, False)):
+        l, u = pb.lb.copy(), pb.ub.copy()
+        u[bad] = l[bad] - 1
+        o = orc.fixpoint(pb, l, u)
+        assert o["failed"] == want_failed
+        with eng.Solver(pb, mem_kind=kind) as s:
+            g = s.propagate(l, u)
+        assert_same_store(g, o, (kind, bad))
+
+
+@pytest.mark.parametrize("fp", [abi.FP_AC1, abi.FP_WAC1])
+@pytest.mark.parametrize("kind", KINDS)
+def test_exact_and_extended_arithmetic_classes_together(eng, orc, kind, fp):
+    """Some variables get infinite or 2^30-sized bounds (extended-integer classes), the others stay small
+    (32-bit classes); constants of every size; one network."""
+    for seed in range(6):
+        pb = tnf_gen.planted(300, 900, 900 + seed, spread=2000, slack=500,
+                             mix={abi.OP_ADD: 0.4, abi.OP_LEQ: 0.2, abi.OP_EQ: 0.15, abi.OP_MIN: 0.05, abi.OP_MAX: 0.05,
+                                  abi.OP_MUL: 0.05, abi.OP_TDIV: 0.05, abi.OP_TMOD: 0.05})
+        rng = np.random.default_rng(seed)
+        lb, ub = pb.lb.astype(np.int64), pb.ub.astype(np.int64)
+        res = {int(p["x"]) for p in pb.props if int(p["op"]) in (abi.OP_EQ, abi.OP_LEQ)}
+        for v in rng.choice(np.arange(3, pb.nvars), size=60, replace=False):
+            if int(v) in res:
+                continue
+            how = rng.integers(0, 4)
+            if how == 0:
+                lb[v] = abi.NEG_INF
+            elif how == 1:
+                ub[v] = abi.POS_INF
+            elif how == 2:
+                lb[v], ub[v] = -(2 ** 30), 2 ** 30
+            else:
+                lb[v], ub[v] = abi.NEG_INF, abi.POS_INF
+        big = abi.Problem(lb, ub, pb.props)
+        classes = {k for k, n in eng.layout_describe(big)["classes"].items() if n}
+        assert {"add_s", "add_g"} <= classes
+        o = orc.fixpoint(big)
+        with eng.Solver(big, mem_kind=kind, fixpoint=fp) as s:
+            g = s.propagate()
+        assert_same_store(g, o, (kind, fp, seed))

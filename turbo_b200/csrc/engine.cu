@@ -978,15 +978,42 @@ struct tb_solver {
   int32_t* h_pinned_one = nullptr;
 };
 
+// Device memory comes from the device's stream-ordered pool with the release threshold lifted, so that
+// creating and destroying solvers (the drop-in call pattern: one solver per model) does not pay
+// cudaMalloc / cudaFree every time: cudaFree of the per-block scratch alone took up to 0.7 s.
+static void retain_pool_memory(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
+
 template <class T>
 static tb_status dev_alloc(tb_solver* s, T** p, size_t count) {
   void* q = nullptr;
   size_t bytes = std::max<size_t>(count * sizeof(T), 16);
-  cudaError_t e = cudaMalloc(&q, bytes);
-  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? TB_ERR_NOMEM : TB_ERR_CUDA; }
+  retain_pool_memory(s->device);
+  cudaError_t e = cudaMallocAsync(&q, bytes, (cudaStream_t)0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);   // usable from the solver's own streams
+  if (e != cudaSuccess) { set_error(std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TB_ERR_NOMEM : TB_ERR_CUDA; }
   s->allocs.push_back(q);
   *p = (T*)q;
   return TB_OK;
+}
+
+// One pinned word holding the constant 1 (source of the asynchronous "stop" copy), shared by all solvers.
+static int32_t* pinned_one() {
+  static int32_t* p = nullptr;
+  if (!p) {
+    if (cudaHostAlloc((void**)&p, 64, cudaHostAllocPortable) != cudaSuccess) { p = nullptr; cudaGetLastError(); }
+    else *p = 1;
+  }
+  return p;
 }
 
 // kernel dispatch over the placement
@@ -1303,7 +1330,8 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (cudaMemcpy(d, hs.data(), hs.size() * sizeof(DevStrategy), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D strategies"); return fail(TB_ERR_CUDA); }
     P.strategies = d; P.nstrategies = pb->nstrategies;
   }
-  if ((rc = dev_alloc(s, &s->d_bound, 32))) return fail(rc);
+  // the incumbent cell is exported to other processes (CUDA IPC): that needs a plain cudaMalloc allocation
+  if (cudaMalloc((void**)&s->d_bound, 128) != cudaSuccess) { set_error("cudaMalloc (incumbent cell) failed"); cudaGetLastError(); return fail(TB_ERR_CUDA); }
   if ((rc = dev_alloc(s, &s->d_stop, 32))) return fail(rc);
   if ((rc = dev_alloc(s, &s->d_next, 4))) return fail(rc);
   P.appx_best_bound = s->d_bound; P.stop = s->d_stop; P.next_subproblem = s->d_next;
@@ -1312,10 +1340,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&s->ev_start) != cudaSuccess || cudaEventCreate(&s->ev_stop) != cudaSuccess ||
-      cudaHostAlloc((void**)&s->h_pinned_one, 64, cudaHostAllocDefault) != cudaSuccess) {
+      (s->h_pinned_one = pinned_one()) == nullptr) {
     set_error("stream/event creation failed"); return fail(TB_ERR_CUDA);
   }
-  *s->h_pinned_one = 1;
 
   // II. number of subproblems (barebones :548-555), generalised to the GPU count
   int d = opt.subproblems_power;
@@ -1335,8 +1362,10 @@ extern "C" void tb_destroy(tb_solver* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (void* h : s->ipc_opened) cudaIpcCloseMemHandle(h);
-  for (void* p : s->allocs) cudaFree(p);
-  if (s->h_pinned_one) cudaFreeHost(s->h_pinned_one);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (void* p : s->allocs) cudaFreeAsync(p, (cudaStream_t)0);     // back to the pool, which keeps it
+  if (s->d_bound) cudaFree(s->d_bound);
+  cudaGetLastError();
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->ev_start) cudaEventDestroy(s->ev_start);
