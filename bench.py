@@ -44,6 +44,8 @@ def load_workload(name):
         _, nv, npr = name.split(":") if ":" in name else (name, "100000", "1000000")
         m = Model.synthetic(int(nv), int(npr), 0xB200)
         return m.problem, dict(objective_kind=-1)
+    if name.startswith("simplified:"):     # the network the TNF simplifier leaves (tests/golden/simplified)
+        return golden_io.load_simplified_problem(name.split(":", 1)[1])
     return golden_io.load(name)
 
 

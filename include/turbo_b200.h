@@ -214,6 +214,31 @@ int32_t tb_model_num_parsed_constraints(const tb_model*);
 /* Root store was found inconsistent while building / preprocessing. */
 int32_t tb_model_root_failed(const tb_model*);
 
+/* ---- TNF simplifier (replaces lala-core's Simplifier as driven by CP::preprocess_tcn,
+ * include/common_solving.hpp:538-565): root fixpoint -> equivalence classes -> algebraic simplification ->
+ * entailed-constraint elimination -> ICSE -> useless-variable elimination, to a fixpoint. The root fixpoint is
+ * the CALLER's (the driver passes tb_propagate on the GPU), so narrowing has one implementation. Afterwards
+ * tb_model_problem() is the reduced network; tb_model_check_solution / _check_tnf / _format_solution still take
+ * stores of tb_model_problem() and expand them to the full network internally. */
+typedef struct {
+  int32_t iterations, vars_before, props_before, vars_after, props_after;
+  int32_t merged_variables;        /* variables that joined another one's equivalence class */
+  int32_t eliminated_equalities;   /* propagators that were equalities in disguise (algebraic simplification) */
+  int32_t eliminated_entailed;     /* propagators entailed by the root store */
+  int32_t eliminated_icse;         /* duplicates of another x = y op z */
+  int32_t eliminated_variables;    /* classes left without any propagator */
+  int32_t root_failed;
+} tb_simplify_stats;
+/* In: a network and its domains in lb/ub. Out: the greatest fixpoint in lb/ub, *failed = 1 if it is empty. */
+typedef tb_status (*tb_fixpoint_fn)(void* ctx, const tb_problem* pb, int32_t* lb, int32_t* ub, int32_t* failed);
+tb_status tb_model_simplify(tb_model*, tb_fixpoint_fn fixpoint, void* ctx, tb_simplify_stats* stats);
+/* tb_fixpoint_fn backed by tb_create + tb_propagate on CUDA device *(int32_t*)ctx (device 0 when ctx is NULL). */
+tb_status tb_fixpoint_on_device(void* ctx, const tb_problem* pb, int32_t* lb, int32_t* ub, int32_t* failed);
+/* Variables of the network as it was built (before simplification). */
+int32_t tb_model_num_full_variables(const tb_model*);
+/* Store of tb_model_problem() -> store of the full network (full_ub may be NULL). */
+tb_status tb_model_expand_solution(const tb_model*, const int32_t* lb, const int32_t* ub, int32_t* full_lb, int32_t* full_ub);
+
 /* Re-check a point (value of var v = lb[v]) against the ORIGINAL FlatZinc constraints; returns the
  * number of violated constraints (0 = valid) or -1 when the model carries no FlatZinc source
  * (synthetic / .tnf models: use tb_model_check_tnf). */

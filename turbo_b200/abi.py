@@ -81,6 +81,15 @@ class TbStats(C.Structure):
         return d
 
 
+class TbSimplifyStats(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("iterations", "vars_before", "props_before", "vars_after", "props_after",
+                                         "merged_variables", "eliminated_equalities", "eliminated_entailed",
+                                         "eliminated_icse", "eliminated_variables", "root_failed")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class TbLayoutInfo(C.Structure):
     _fields_ = [("nclasses", C.c_int32), ("nchunks", C.c_int32), ("nslots", C.c_int32), ("identity", C.c_int32),
                 ("class_count", C.c_int32 * 32), ("loads_per_sweep", C.c_uint64), ("wavefronts_per_load", C.c_double)]

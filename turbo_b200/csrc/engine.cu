@@ -1705,3 +1705,25 @@ extern "C" tb_status tb_read_bound(tb_solver* s, int32_t* bound) {
   CU(cudaMemcpy(bound, s->d_bound, sizeof(int), cudaMemcpyDeviceToHost));
   return TB_OK;
 }
+
+// ---- the engine's fixpoint as a tb_fixpoint_fn (root fixpoint of the TNF simplifier, tnf_simplify.cpp) ------
+extern "C" tb_status tb_fixpoint_on_device(void* ctx, const tb_problem* pb, int32_t* lb, int32_t* ub, int32_t* failed) {
+  if (!pb || !lb || !ub || !failed) { set_error("tb_fixpoint_on_device: null argument"); return TB_ERR_INVALID; }
+  tb_options o;
+  memset(&o, 0, sizeof(o));
+  o.fixpoint = TB_FP_WAC1; o.subproblems_power = 0; o.subproblems_factor = 300; o.mem_kind = TB_MEM_AUTO; o.gpu_world = 1;
+  o.or_blocks = 1;
+  o.device = ctx ? *(const int32_t*)ctx : 0;
+  tb_problem q = *pb;
+  q.lb = lb; q.ub = ub;
+  tb_solver* s = nullptr;
+  tb_status rc = tb_create(&s, &q, &o);
+  if (rc != TB_OK) return rc;
+  std::vector<int32_t> olb((size_t)std::max(1, pb->nvars)), oub((size_t)std::max(1, pb->nvars));
+  tb_stats st;
+  rc = tb_propagate(s, nullptr, nullptr, olb.data(), oub.data(), failed, &st);
+  tb_destroy(s);
+  if (rc != TB_OK) return rc;
+  if (!*failed && pb->nvars) { memcpy(lb, olb.data(), (size_t)pb->nvars * 4); memcpy(ub, oub.data(), (size_t)pb->nvars * 4); }
+  return TB_OK;
+}

@@ -187,6 +187,13 @@ tb_status tb_model_push_eps_strategy(tb_model* m, int32_t var_order, int32_t val
 int32_t tb_model_check_tnf(const tb_model* m, const int32_t* lb) {
   if (!m || !lb) return -1;
   int bad = 0;
+  if (m->simplified) {             // expand to the full network and check every original propagator there
+    std::vector<int32_t> flb, fub;
+    tb_model_expand_internal(m, lb, nullptr, flb, fub);
+    for (size_t v = 0; v < flb.size(); ++v) bad += (flb[v] < m->full_lb[v] || flb[v] > m->full_ub[v]) ? 1 : 0;
+    for (const tb_prop& p : m->full_props) bad += prop_holds(p, flb.data()) ? 0 : 1;
+    return bad;
+  }
   for (size_t v = 0; v < m->lb.size(); ++v) bad += (lb[v] < m->lb[v] || lb[v] > m->ub[v]) ? 1 : 0;
   for (const tb_prop& p : m->props) bad += prop_holds(p, lb) ? 0 : 1;
   return bad;
@@ -195,6 +202,8 @@ int32_t tb_model_check_tnf(const tb_model* m, const int32_t* lb) {
 int32_t tb_model_check_solution(const tb_model* m, const int32_t* lb, const int32_t* ub) {
   (void)ub;
   if (!m || !lb || !m->src) return -1;
+  std::vector<int32_t> flb, fub;
+  if (m->simplified) { tb_model_expand_internal(m, lb, nullptr, flb, fub); lb = flb.data(); }
   std::vector<int64_t> value(m->src->vars.size());
   for (size_t i = 0; i < value.size(); ++i) value[i] = lb[m->var_of_model[i]];
   try {
@@ -213,6 +222,8 @@ int32_t tb_model_check_solution(const tb_model* m, const int32_t* lb, const int3
 size_t tb_model_format_solution(const tb_model* m, const int32_t* lb, const int32_t* ub, char* buf, size_t cap) {
   (void)ub;
   if (!m || !lb || !m->src) return 0;
+  std::vector<int32_t> flb, fub;
+  if (m->simplified) { tb_model_expand_internal(m, lb, nullptr, flb, fub); lb = flb.data(); }
   const fzn::Model& src = *m->src;
   std::string s;
   auto value_of = [&](const fzn::Expr& e, bool is_bool) -> std::string {

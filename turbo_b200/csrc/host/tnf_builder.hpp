@@ -31,6 +31,13 @@ struct tb_model {
   bool root_failed = false;
   int parsed_variables = 0, parsed_constraints = 0;
   std::string error;
+  // ---- set by tb_model_simplify (tnf_simplify.cpp): lb/ub/props/strategies above then describe the REDUCED
+  // network; the full one (what var_of_model indexes) is kept here for printing and re-checking ------------
+  bool simplified = false;
+  tb_simplify_stats simplify_stats{};
+  std::vector<int32_t> full_lb, full_ub;     // root-propagated domains of the full network
+  std::vector<tb_prop> full_props;
+  std::vector<int32_t> red_of_full;          // full variable -> reduced variable, -1 = eliminated (takes full_lb)
 
   void finalize();                           // (re)build `problem` from the vectors
   // Prepend the EPS strategy (-eps_var_order / -eps_value_order, common_solving.hpp:652-667).
@@ -39,6 +46,9 @@ struct tb_model {
 
 // Throws std::runtime_error on unsupported constraints.
 std::unique_ptr<tb_model> build_tnf(std::unique_ptr<fzn::Model> src);
+
+// Store of the reduced network -> point of the full one (tnf_simplify.cpp).
+void tb_model_expand_internal(const tb_model* m, const int32_t* lb, const int32_t* ub, std::vector<int32_t>& flb, std::vector<int32_t>& fub);
 
 // Number of violated FlatZinc constraints / domains at the point value[v] (FlatZinc variable index).
 int check_flatzinc(const fzn::Model& m, const std::vector<int64_t>& value, std::string* first_violation);

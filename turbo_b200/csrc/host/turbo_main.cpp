@@ -325,6 +325,24 @@ int main(int argc, char** argv) {
   S.s("entailed_prop_removal", "deactivated");
   S.u("tcn_variables", (uint64_t)pb->nvars);
   S.u("tcn_constraints", (uint64_t)pb->nprops);
+  // TNF simplifier (preprocess_tcn, common_solving.hpp:538-565); its root fixpoint runs on the GPU
+  if (!config.disable_simplify && !tb_model_root_failed(model)) {
+    if (tb_device_count() <= 0) { std::cerr << "No CUDA device found: turbo (B200 build) has no CPU fallback." << std::endl; return EXIT_FAILURE; }
+    int32_t dev = 0;
+    tb_simplify_stats ss;
+    rc = tb_model_simplify(model, tb_fixpoint_on_device, &dev, &ss);
+    if (rc != TB_OK) { std::cerr << "tb_model_simplify failed: " << tb_last_error() << std::endl; return EXIT_FAILURE; }
+    pb = tb_model_problem(model);
+    S.i("preprocessing_iterations", ss.iterations);
+    S.i("preprocessing_icse_eliminated_constraints", ss.eliminated_icse);
+    S.i("preprocessing_algsimp_eliminated_constraints", ss.eliminated_equalities);
+    S.i("preprocessing_algsimp_eliminated_eq_constraints", ss.merged_variables);
+    S.i("preprocessing_entailment_eliminated_constraints", ss.eliminated_entailed);
+    S.i("preprocessing_eliminated_variables", ss.eliminated_variables + ss.merged_variables);
+    S.u("preprocessed_tcn_variables", (uint64_t)pb->nvars);
+    S.u("preprocessed_tcn_constraints", (uint64_t)pb->nprops);
+    if (config.verbose) printf("%% Formula simplified.\n");
+  }
   const int64_t init_ns = since_ns();
   S.d("preprocessing_time", to_sec(init_ns));
   S.end();

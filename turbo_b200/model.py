@@ -8,6 +8,8 @@ from . import abi
 from .engine import TurboError, lib
 
 _INIT = False
+FIXPOINT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(abi.TbProblem), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                          C.POINTER(C.c_int32))
 
 
 def _lib():
@@ -33,6 +35,12 @@ def _lib():
         L.tb_model_check_tnf.restype = C.c_int32
         L.tb_model_format_solution.argtypes = [vp, i32p, i32p, C.c_char_p, C.c_size_t]
         L.tb_model_format_solution.restype = C.c_size_t
+        L.tb_model_simplify.argtypes = [vp, vp, vp, C.POINTER(abi.TbSimplifyStats)]
+        L.tb_model_simplify.restype = C.c_int
+        L.tb_model_num_full_variables.argtypes = [vp]
+        L.tb_model_num_full_variables.restype = C.c_int32
+        L.tb_model_expand_solution.argtypes = [vp, i32p, i32p, i32p, i32p]
+        L.tb_model_expand_solution.restype = C.c_int
         L.tb_model_destroy.argtypes = [vp]
         L.tb_model_destroy.restype = None
         _INIT = True
@@ -90,6 +98,60 @@ class Model:
     def push_eps_strategy(self, var_order, val_order):
         _lib().tb_model_push_eps_strategy(self._h, var_order, val_order)
         self._refresh()
+
+    def simplify(self, fixpoint="device", device=0):
+        """TNF simplifier (tb_model_simplify). `fixpoint` is "device" (the engine's tb_propagate on a GPU, what
+        the `turbo` driver uses) or a callable (problem: abi.Problem) -> (lb, ub, failed) — tests pass the oracle.
+        Afterwards `self.problem` is the reduced network."""
+        L = _lib()
+        st = abi.TbSimplifyStats()
+        if fixpoint == "device":
+            dev = C.c_int32(device)
+            fn = C.cast(L.tb_fixpoint_on_device, C.c_void_p)
+            rc = L.tb_model_simplify(self._h, fn, C.cast(C.byref(dev), C.c_void_p), C.byref(st))
+        else:
+            i32p = C.POINTER(C.c_int32)
+            err = []
+
+            @FIXPOINT_FN
+            def cb(ctx, pbp, lbp, ubp, failedp):
+                try:
+                    pb = abi.Problem.from_c(pbp)
+                    n = pb.nvars
+                    lb = np.ctypeslib.as_array(lbp, shape=(max(1, n),))
+                    ub = np.ctypeslib.as_array(ubp, shape=(max(1, n),))
+                    nlb, nub, failed = fixpoint(pb)
+                    failedp[0] = 1 if failed else 0
+                    if not failed and n:
+                        lb[:n] = nlb[:n]
+                        ub[:n] = nub[:n]
+                    return 0
+                except Exception as e:      # never unwind through C
+                    err.append(e)
+                    return abi.ERR_INVALID if hasattr(abi, "ERR_INVALID") else 1
+            rc = L.tb_model_simplify(self._h, C.cast(cb, C.c_void_p), None, C.byref(st))
+            if err:
+                raise err[0]
+        if rc != 0:
+            raise TurboError(rc, lib().tb_last_error().decode())
+        self._refresh()
+        self.simplify_stats = st.as_dict()
+        return self.simplify_stats
+
+    @property
+    def num_full_variables(self):
+        return int(_lib().tb_model_num_full_variables(self._h))
+
+    def expand(self, lb, ub=None):
+        """Store of `self.problem` (possibly reduced) -> store of the network as it was built."""
+        lb = np.ascontiguousarray(lb, dtype=np.int32)
+        ub = lb if ub is None else np.ascontiguousarray(ub, dtype=np.int32)
+        n = max(1, self.num_full_variables)
+        flb, fub = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        rc = _lib().tb_model_expand_solution(self._h, _p(lb), _p(ub), _p(flb), _p(fub))
+        if rc != 0:
+            raise TurboError(rc, lib().tb_last_error().decode())
+        return flb[:self.num_full_variables], fub[:self.num_full_variables]
 
     def check_solution(self, lb, ub=None):
         """Violated FlatZinc constraints at the point lb (0 = valid; -1 = no FlatZinc source)."""
