@@ -227,6 +227,7 @@ typedef struct {
   int32_t eliminated_entailed;     /* propagators entailed by the root store */
   int32_t eliminated_icse;         /* duplicates of another x = y op z */
   int32_t eliminated_variables;    /* classes left without any propagator */
+  int32_t eliminated_functional;   /* x = y op z whose x occurs nowhere else and cannot prune: x is computed at expansion */
   int32_t root_failed;
 } tb_simplify_stats;
 /* In: a network and its domains in lb/ub. Out: the greatest fixpoint in lb/ub, *failed = 1 if it is empty. */

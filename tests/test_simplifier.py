@@ -112,6 +112,25 @@ def test_equivalences_constants_and_useless_variables():
     assert vals["x"] == vals["y"] and vals["s"] == vals["t"] == "3" and vals["w"] == "0"
 
 
+def test_functionally_defined_variables_are_computed_at_expansion():
+    # d = x + z and e = (d <= 7) are only defined, never used: both propagators go, the values come back on expansion
+    m = Model.from_fzn_text(
+        "var 0..9: x :: output_var;\nvar 0..9: z :: output_var;\nvar 0..18: d :: output_var;\nvar bool: e :: output_var;\n"
+        "constraint int_lin_eq([1,1,-1],[x,z,d],0);\nconstraint int_le_reif(d, 7, e);\nconstraint int_lin_le([-1,-2],[x,z],-11);\n"
+        "solve minimize x;\n")
+    st = m.simplify(oracle_fixpoint)
+    assert st["eliminated_functional"] == 2
+    from oracle import oracle_py as orc
+    r = orc.solve(m.problem, depth=0)
+    assert r["has_solution"] and m.check_solution(r["lb"]) == 0 and m.check_tnf(r["lb"]) == 0
+    vals = dict(line.rstrip(";").split(" = ") for line in m.format_solution(r["lb"]).strip().splitlines())
+    assert int(vals["d"]) == int(vals["x"]) + int(vals["z"]) and vals["e"] == ("true" if int(vals["d"]) <= 7 else "false")
+    # a defined variable whose domain is tighter than the range of its definition is a constraint: it stays
+    m = Model.from_fzn_text("var 0..9: x;\nvar 0..9: z;\nvar 0..5: d;\nconstraint int_lin_eq([1,1,-1],[x,z,d],0);\nsolve maximize x;\n")
+    st = m.simplify(oracle_fixpoint)
+    assert st["eliminated_functional"] == 0 and m.problem.nprops >= 1
+
+
 def test_root_failure_is_detected_by_the_simplifier():
     m = Model.from_fzn_text("var 0..5: x;\nvar 0..5: y;\nconstraint int_lin_eq([1,1],[x,y],20);\nsolve satisfy;\n")
     m.simplify(oracle_fixpoint)

@@ -84,7 +84,7 @@ class TbStats(C.Structure):
 class TbSimplifyStats(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("iterations", "vars_before", "props_before", "vars_after", "props_after",
                                          "merged_variables", "eliminated_equalities", "eliminated_entailed",
-                                         "eliminated_icse", "eliminated_variables", "root_failed")]
+                                         "eliminated_icse", "eliminated_variables", "eliminated_functional", "root_failed")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -37,7 +37,9 @@ struct tb_model {
   tb_simplify_stats simplify_stats{};
   std::vector<int32_t> full_lb, full_ub;     // root-propagated domains of the full network
   std::vector<tb_prop> full_props;
-  std::vector<int32_t> red_of_full;          // full variable -> reduced variable, -1 = eliminated (takes full_lb)
+  std::vector<int32_t> red_of_full;          // full variable -> reduced variable, -1 = eliminated (takes full_lb, or its definition)
+  std::vector<int32_t> rep_of_full;          // full variable -> representative of its equivalence class (full index)
+  std::vector<tb_prop> defs;                 // x = y op z of functionally defined variables (full indices of representatives)
 
   void finalize();                           // (re)build `problem` from the vectors
   // Prepend the EPS strategy (-eps_var_order / -eps_value_order, common_solving.hpp:652-667).

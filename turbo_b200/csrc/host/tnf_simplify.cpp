@@ -29,6 +29,7 @@ struct Simplifier {
   std::vector<tb_prop> ps;            // operands are always representatives
   bool failed = false;
   tb_simplify_stats st{};
+  std::vector<tb_prop> defs;          // propagators removed by eliminate_functional, in elimination order
 
   int find(int v) {
     while (parent[(size_t)v] != v) { parent[(size_t)v] = parent[(size_t)parent[(size_t)v]]; v = parent[(size_t)v]; }
@@ -126,13 +127,22 @@ struct Simplifier {
         case TB_OP_ADD:
           if (fixed_to(p.z, 0)) { changed |= unite(p.x, p.y); drop = true; }
           else if (fixed_to(p.y, 0)) { changed |= unite(p.x, p.z); drop = true; }
+          else if (p.x == p.y && lb[(size_t)p.x] != INT32_MIN && ub[(size_t)p.x] != INT32_MAX) { changed |= meet(p.z, 0, 0); drop = true; }   // x = x + z
+          else if (p.x == p.z && lb[(size_t)p.x] != INT32_MIN && ub[(size_t)p.x] != INT32_MAX) { changed |= meet(p.y, 0, 0); drop = true; }
           break;
         case TB_OP_MUL:
           if (fixed_to(p.z, 1)) { changed |= unite(p.x, p.y); drop = true; }
           else if (fixed_to(p.y, 1)) { changed |= unite(p.x, p.z); drop = true; }
+          else if (fixed_to(p.y, 0) || fixed_to(p.z, 0)) { changed |= meet(p.x, 0, 0); drop = true; }
           break;
-        case TB_OP_MIN: case TB_OP_MAX:
-          if (p.y == p.z) { changed |= unite(p.x, p.y); drop = true; }
+        case TB_OP_MIN:
+          // one operand never exceeds the other: the minimum IS that operand (conjunctions with a constant true, ...)
+          if (p.y == p.z || ub[(size_t)p.y] <= lb[(size_t)p.z]) { changed |= unite(p.x, p.y); drop = true; }
+          else if (ub[(size_t)p.z] <= lb[(size_t)p.y]) { changed |= unite(p.x, p.z); drop = true; }
+          break;
+        case TB_OP_MAX:
+          if (p.y == p.z || lb[(size_t)p.y] >= ub[(size_t)p.z]) { changed |= unite(p.x, p.y); drop = true; }
+          else if (lb[(size_t)p.z] >= ub[(size_t)p.y]) { changed |= unite(p.x, p.z); drop = true; }
           break;
         default: break;
       }
@@ -177,7 +187,68 @@ struct Simplifier {
     }
     return changed;
   }
+
+  // Does dom(x) contain every value y op z can take on the current box?  Then the propagator never prunes y or z.
+  bool covers(const tb_prop& p) const {
+    const int64_t yl = lb[(size_t)p.y], yu = ub[(size_t)p.y], zl = lb[(size_t)p.z], zu = ub[(size_t)p.z];
+    const bool finite = yl != INT32_MIN && yu != INT32_MAX && zl != INT32_MIN && zu != INT32_MAX;
+    int64_t lo, hi;
+    switch (p.op) {
+      case TB_OP_ADD: if (!finite) return false; lo = yl + zl; hi = yu + zu; break;
+      case TB_OP_MUL: {
+        if (!finite) return false;
+        const int64_t c[4] = {yl * zl, yl * zu, yu * zl, yu * zu};
+        lo = *std::min_element(c, c + 4); hi = *std::max_element(c, c + 4);
+        break;
+      }
+      case TB_OP_MIN: lo = std::min(yl, zl); hi = std::min(yu, zu); break;
+      case TB_OP_MAX: lo = std::max(yl, zl); hi = std::max(yu, zu); break;
+      case TB_OP_EQ: case TB_OP_LEQ: lo = 0; hi = 1; break;
+      default: return false;
+    }
+    return (int64_t)lb[(size_t)p.x] <= lo && (int64_t)ub[(size_t)p.x] >= hi;
+  }
+
+  // Functionally defined variables: x occurs in one propagator only, as its result, and its domain covers the
+  // range of y op z.  The propagator can then never prune anything: drop it and compute x when a solution is
+  // expanded.  Dropping it may leave y or z in the same situation (cascade).  `keep` marks variables the engine
+  // needs (objective, the constants 0, 1, 2).
+  void eliminate_functional(const std::vector<char>& keep) {
+    std::vector<int> occ(parent.size(), 0);
+    for (const tb_prop& p : ps) { ++occ[(size_t)p.x]; ++occ[(size_t)p.y]; ++occ[(size_t)p.z]; }
+    std::vector<char> dead(ps.size(), 0);
+    bool again = true;
+    while (again) {
+      again = false;
+      for (size_t i = 0; i < ps.size(); ++i) {
+        if (dead[i]) continue;
+        const tb_prop& p = ps[i];
+        if (occ[(size_t)p.x] != 1 || keep[(size_t)p.x] || fixed(p.x) || !covers(p)) continue;
+        dead[i] = 1;
+        defs.push_back(p);
+        --occ[(size_t)p.x]; --occ[(size_t)p.y]; --occ[(size_t)p.z];
+        ++st.eliminated_functional;
+        again = true;
+      }
+    }
+    std::vector<tb_prop> keep_ps;
+    keep_ps.reserve(ps.size());
+    for (size_t i = 0; i < ps.size(); ++i) if (!dead[i]) keep_ps.push_back(ps[i]);
+    ps.swap(keep_ps);
+  }
 };
+
+int64_t eval_op(int op, int64_t y, int64_t z) {
+  switch (op) {
+    case TB_OP_ADD: return y + z;
+    case TB_OP_MUL: return y * z;
+    case TB_OP_MIN: return std::min(y, z);
+    case TB_OP_MAX: return std::max(y, z);
+    case TB_OP_EQ: return y == z ? 1 : 0;
+    case TB_OP_LEQ: return y <= z ? 1 : 0;
+    default: return 0;
+  }
+}
 
 }  // namespace
 
@@ -245,7 +316,17 @@ extern "C" tb_status tb_model_simplify(tb_model* m, tb_fixpoint_fn fixpoint, voi
   m->full_lb = m->lb; m->full_ub = m->ub; m->full_props = m->props;
   m->root_failed = m->root_failed || s.failed;
   s.substitute();
+  if (!m->root_failed) {
+    std::vector<char> keep((size_t)V, 0);
+    for (int k = 0; k < 3 && k < V; ++k) keep[(size_t)s.find(k)] = 1;
+    if (m->obj_var >= 0) keep[(size_t)s.find(m->obj_var)] = 1;
+    if (m->user_obj_var >= 0) keep[(size_t)s.find(m->user_obj_var)] = 1;
+    s.eliminate_functional(keep);
+  }
   compact(true);
+  m->rep_of_full.resize((size_t)V);
+  for (int v = 0; v < V; ++v) m->rep_of_full[(size_t)v] = s.find(v);
+  m->defs = s.defs;
   m->red_of_full.assign((size_t)V, -1);
   for (int v = 0; v < V; ++v) {
     const int r = s.find(v);
@@ -289,10 +370,22 @@ extern "C" tb_status tb_model_simplify(tb_model* m, tb_fixpoint_fn fixpoint, voi
 void tb_model_expand_internal(const tb_model* m, const int32_t* lb, const int32_t* ub, std::vector<int32_t>& flb, std::vector<int32_t>& fub) {
   const size_t V = m->red_of_full.size();
   flb.resize(V); fub.resize(V);
+  // values of the class representatives: from the store, or the root domain when nothing constrains the class
   for (size_t v = 0; v < V; ++v) {
+    if ((size_t)m->rep_of_full[v] != v) continue;
     const int32_t d = m->red_of_full[v];
     if (d >= 0) { flb[v] = lb[d]; fub[v] = ub ? ub[d] : lb[d]; }
     else { flb[v] = m->full_lb[v]; fub[v] = m->full_ub[v]; }
+  }
+  // functionally defined variables, innermost definition last: evaluate in reverse elimination order at the point lb
+  for (size_t i = m->defs.size(); i-- > 0;) {
+    const tb_prop& p = m->defs[i];
+    const int32_t x = (int32_t)eval_op(p.op, flb[(size_t)p.y], flb[(size_t)p.z]);
+    flb[(size_t)p.x] = x; fub[(size_t)p.x] = x;
+  }
+  for (size_t v = 0; v < V; ++v) {
+    const size_t r = (size_t)m->rep_of_full[v];
+    if (r != v) { flb[v] = flb[r]; fub[v] = fub[r]; }
   }
 }
 

@@ -338,6 +338,7 @@ int main(int argc, char** argv) {
     S.i("preprocessing_algsimp_eliminated_constraints", ss.eliminated_equalities);
     S.i("preprocessing_algsimp_eliminated_eq_constraints", ss.merged_variables);
     S.i("preprocessing_entailment_eliminated_constraints", ss.eliminated_entailed);
+    S.i("preprocessing_functional_eliminated_constraints", ss.eliminated_functional);
     S.i("preprocessing_eliminated_variables", ss.eliminated_variables + ss.merged_variables);
     S.u("preprocessed_tcn_variables", (uint64_t)pb->nvars);
     S.u("preprocessed_tcn_constraints", (uint64_t)pb->nprops);

@@ -11,7 +11,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libturbo_b200.so")
+# TURBO_B200_LIB selects another build of the same library (A/B runs of kernel variants); there is still no fallback.
+LIB_PATH = os.environ.get("TURBO_B200_LIB") or os.path.join(_HERE, "libturbo_b200.so")
 _LIB = None
 
 
