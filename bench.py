@@ -136,6 +136,9 @@ def run_ours(args):
         opts["threads_per_block"] = args.tpb
     if args.blocks:
         opts["or_blocks"] = args.blocks
+    if args.mem != "auto":
+        opts["mem_kind"] = {"global": abi.MEM_GLOBAL, "store_shared": abi.MEM_STORE_SHARED, "tcn_shared": abi.MEM_TCN_SHARED,
+                            "store_cluster": abi.MEM_STORE_CLUSTER}[args.mem]
     solver = engine.Solver(pb, **opts)
     if world > 1:
         handles = [None] * world
@@ -307,6 +310,7 @@ def main():
     ap.add_argument("--fp", default="wac1", choices=["ac1", "wac1"])
     ap.add_argument("--tpb", type=int, default=0)
     ap.add_argument("--blocks", type=int, default=0)
+    ap.add_argument("--mem", default="auto", choices=["auto", "global", "store_shared", "tcn_shared", "store_cluster"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixpoint-leg", action="store_true")
     args = ap.parse_args()

@@ -1087,8 +1087,11 @@ static tb_status configure(tb_solver* s) {
     }
   }
   if (kind == TB_MEM_AUTO) {
-    // Prefer the propagator table in shared memory unless that costs most of the resident blocks.
-    if (b_tcn >= 1 && (b_tcn >= 4 || b_tcn * 2 >= std::min(b_store, 8))) kind = TB_MEM_TCN_SHARED;
+    // Prefer the propagator table in shared memory unless that leaves a single resident block where the store alone
+    // allows two: two half-size blocks hide each other's sweep barriers, which is worth more than the L2 stream costs
+    // (measured on the simplified trains15 network: 3.55 M nodes/s with 2 x 512 threads against 2.93 M with the table
+    // in shared memory and 1 x 1024, profiles/r01_placement_experiments.txt).
+    if (b_tcn >= 1 && !(b_tcn == 1 && b_store >= 2) && (b_tcn >= 4 || b_tcn * 2 >= std::min(b_store, 8))) kind = TB_MEM_TCN_SHARED;
     else if (b_store >= 1) kind = TB_MEM_STORE_SHARED;
     else if (cluster >= 2) kind = TB_MEM_STORE_CLUSTER;    // the store is larger than one SM: stripe it over DSMEM
     else kind = TB_MEM_GLOBAL;
@@ -1118,8 +1121,11 @@ static tb_status configure(tb_solver* s) {
   // Threads: keep ~1024 resident threads per SM at <= 64 registers (the reference compiles 256/block).
   int threads = s->opt.threads_per_block;
   if (threads <= 0) {
+    // 1024 resident threads per SM (64 registers each), spread over as many blocks as shared memory allows, up to
+    // 8 x 128: small networks are bound by the barriers and the one-thread sections of the search, which more
+    // independent blocks overlap (accap_a3: 21.1 M nodes/s with 8 x 128 against 13.9 M with 4 x 256).
     bps = std::min(bps, 8);
-    threads = bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024);
+    threads = bps >= 8 ? 128 : (bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024));
     threads = std::min(threads, TB_MAX_THREADS);
     // do not use more threads than there is work per sweep
     while (threads > 128 && threads / 2 >= s->P.nchunks * 32) threads /= 2;   // at least one chunk per warp
