@@ -4,8 +4,9 @@ search nodes/s), measured through the C ABI of libturbo_b200.so.
 
 A *step* is one bounded dive-and-solve pass (`tb_solve` with a per-block node budget, the
 reference's `-cutnodes`) over the trains15 TNF network (BASELINE config 2, the configuration the
-metric is quoted on; fixture tests/golden/trains15.npz produced by our front-end from
-benchmarks/trains15.fzn).  `value` counts propagations (one evaluation of one TNF propagator,
+metric is quoted on) as the driver solves it by default: ternarised by our front-end from
+benchmarks/trains15.fzn and reduced by the TNF simplifier (fixture tests/golden/simplified/trains15.npz;
+`--workload trains15` is the network -disable_simplify leaves, reported as `unsimplified_network`).  `value` counts propagations (one evaluation of one TNF propagator,
 the reference's `num_deductions`, include/statistics.hpp:151,354) over the device time of the solve
 kernel with the network already resident in HBM; `e2e` runs the same step from host buffers
 through tb_create + tb_solve + result read-back + tb_destroy.
@@ -108,6 +109,36 @@ def reduce_over_ranks(dist, sums, maxes, device="cpu"):
     return [float(x) for x in t.tolist()], [float(x) for x in m.tolist()]
 
 
+def data_description(workload):
+    if workload.startswith("synthetic"):
+        return "synthetic"
+    if workload.startswith("simplified:"):
+        return ("tests/golden/simplified fixture (TNF of the reference's benchmarks/%s.fzn after the TNF simplifier, "
+                "the network the driver solves by default)" % workload.split(":", 1)[1])
+    return "tests/golden fixture (TNF of the reference's benchmarks/%s.fzn, as with -disable_simplify)" % workload
+
+
+def side_leg(engine, pb, opts, steps, flush, sm_mhz, world=1):
+    """A short run of the same step on another network (reported next to the headline, not as it)."""
+    with engine.Solver(pb, **opts) as s:
+        cfg = s.config()
+        ms, ded, nodes, narrowed = 0.0, 0, 0, 0
+        for i in range(steps + 1):
+            flush.fill_(1)
+            import torch
+            torch.cuda.synchronize()
+            st = s.solve()["stats"]
+            if i == 0:
+                continue                      # warm-up
+            ms += st["kernel_ms"]; ded += st["num_deductions"]; nodes += st["nodes"]; narrowed += st["bounds_narrowed"]
+    secs = ms / 1e3
+    peak = SMEM_BYTES_PER_CLK_PER_SM * SM_COUNT * world * (sm_mhz or 1965.0) * 1e6 / 1e9
+    return {"nvars": pb.nvars, "nprops": pb.nprops, "steps": steps, "memory_configuration": abi.MEM_NAMES.get(cfg["mem_kind"], "?"),
+            "num_blocks_per_gpu": cfg["num_blocks"], "threads_per_block": cfg["threads_per_block"],
+            "value": ded / secs, "unit": "propagations/s", "nodes_per_sec": nodes / secs, "ms_per_step": ms / steps,
+            "roofline_frac": (24.0 * ded + 4.0 * narrowed) / secs / 1e9 / peak}
+
+
 def problem_bytes(pb):
     return int(pb.lb.nbytes + pb.ub.nbytes + pb.props.nbytes + sum(v.nbytes for _, _, v in pb.strategies))
 
@@ -131,7 +162,7 @@ def run_ours(args):
 
     pb, info = load_workload(args.workload)
     opts = dict(device=local, gpu_rank=rank, gpu_world=world, cutnodes=args.cutnodes,
-                fixpoint=abi.FP_AC1 if args.fp == "ac1" else abi.FP_WAC1)
+                fixpoint=abi.FP_KINDS[args.fp])
     if args.tpb:
         opts["threads_per_block"] = args.tpb
     if args.blocks:
@@ -214,8 +245,7 @@ def run_ours(args):
         line = {
             "metric": "propagations/sec", "value": ded / secs if secs > 0 else 0.0, "unit": "propagations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic"
-            if args.workload.startswith("synthetic") else "tests/golden fixture (TNF of the reference's benchmarks/%s.fzn)" % args.workload,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": data_description(args.workload),
             "config": {"workload": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "cutnodes_per_block": args.cutnodes,
                        "fixpoint": args.fp, "num_blocks_per_gpu": cfg["num_blocks"], "threads_per_block": cfg["threads_per_block"],
                        "memory_configuration": abi.MEM_NAMES.get(cfg["mem_kind"], "?"), "subproblems_power": cfg["subproblems_power"],
@@ -238,10 +268,19 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(pb, cfg["subproblems_power"], args)
     solver.close()
     if rank == 0 and world == 1 and not args.no_fixpoint_leg:
-        # the fixpoint kernel alone (the kernel SURVEY.md 8(d)'s shared-memory roofline is stated for)
+        # the fixpoint kernel alone (the kernel SURVEY.md 8(d)'s shared-memory roofline is stated for): root fixpoints of
+        # the FULL network (a simplified network is already at its root fixpoint: one sweep and nothing to narrow)
         from tools.fixpoint_bench import measure
-        line["fixpoint_kernel"] = measure(pb, repeat=20, fp=args.fp, tpb=args.tpb, blocks=args.blocks, device=local,
+        fpb, fname = pb, args.workload
+        if args.workload.startswith("simplified:"):
+            fname = args.workload.split(":", 1)[1]
+            fpb, _ = golden_io.load(fname)
+        line["fixpoint_kernel"] = measure(fpb, repeat=20, fp=args.fp, tpb=args.tpb, blocks=args.blocks, device=local,
                                           sm_mhz=clocks["sm_mhz"])
+        line["fixpoint_kernel"]["network"] = fname
+        if args.workload.startswith("simplified:"):
+            # the same step on the network as -disable_simplify leaves it (the r01 headline before the simplifier existed)
+            line["unsimplified_network"] = side_leg(engine, fpb, opts, min(args.steps, 3), flush, clocks["sm_mhz"])
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -290,7 +329,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "propagations/sec", "value": value, "unit": "propagations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "tests/golden fixture (TNF of the reference's benchmarks/%s.fzn)" % args.workload,
+            "data": data_description(args.workload),
             "config": {"workload": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "step": f"{budget_ms} ms of CPU dive-and-solve"},
             "nodes_per_sec": nodes / secs,
             "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": cores, "kind": "port",
@@ -305,9 +344,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="trains15")
+    ap.add_argument("--workload", default="simplified:trains15",
+                    help="golden fixture name, simplified:<name> (the network the TNF simplifier leaves: what `turbo file.fzn` "
+                         "solves by default, as the reference does unless -disable_simplify), or synthetic[:V:P]")
     ap.add_argument("--cutnodes", type=int, default=2000)
-    ap.add_argument("--fp", default="wac1", choices=["ac1", "wac1"])
+    ap.add_argument("--fp", default="wac1", choices=["ac1", "wac1", "ac1_active", "wac1_active"])
     ap.add_argument("--tpb", type=int, default=0)
     ap.add_argument("--blocks", type=int, default=0)
     ap.add_argument("--mem", default="auto", choices=["auto", "global", "store_shared", "tcn_shared", "store_cluster"])

@@ -64,7 +64,12 @@ typedef struct {
   int32_t obj_var;                /* -1 = satisfaction; always minimised (:439-443) */
 } tb_problem;
 
-typedef enum { TB_FP_AC1 = 0, TB_FP_WAC1 = 1 } tb_fixpoint_kind;
+/* AC1 / WAC1: the reference's block fixpoints (every sweep evaluates every propagator, include/config.hpp:91-97).
+ * The ..._ACTIVE kinds (the reference's FixpointSubsetGPU idea, barebones :636,984) keep the same
+ * sweeps but a warp only evaluates the chunks of 32 propagators one of whose variables changed since the chunk was
+ * last evaluated; same fixpoints, same search, fewer evaluations (num_deductions counts what was evaluated). They
+ * apply to the shared-memory placements; elsewhere they behave like the plain kinds. */
+typedef enum { TB_FP_AC1 = 0, TB_FP_WAC1 = 1, TB_FP_AC1_ACTIVE = 2, TB_FP_WAC1_ACTIVE = 3 } tb_fixpoint_kind;
 
 /* Store placement (MemoryKind, include/memory_gpu.hpp:18-22) plus the B200 cluster/DSMEM tier. */
 typedef enum { TB_MEM_AUTO = -1, TB_MEM_GLOBAL = 0, TB_MEM_STORE_SHARED = 1, TB_MEM_TCN_SHARED = 2,

@@ -22,7 +22,7 @@ MEM = {"auto": abi.MEM_AUTO, "global": abi.MEM_GLOBAL, "store_shared": abi.MEM_S
 
 def measure(pb, repeat=20, fp="wac1", mem="auto", tpb=0, blocks=0, device=0, rounds=3, sm_mhz=None):
     from turbo_b200 import engine
-    opts = dict(device=device, propagate_repeat=repeat, fixpoint=abi.FP_AC1 if fp == "ac1" else abi.FP_WAC1, mem_kind=MEM[mem])
+    opts = dict(device=device, propagate_repeat=repeat, fixpoint=abi.FP_KINDS[fp], mem_kind=MEM[mem])
     if tpb:
         opts["threads_per_block"] = tpb
     if blocks:

@@ -28,7 +28,7 @@ def main():
     pb, info = (golden_io.load_simplified_problem(a.workload.split(':', 1)[1]) if a.workload.startswith('simplified:')
                 else golden_io.load(a.workload))
     with engine.Solver(pb, device=a.device, timeout_ms=a.timeout_ms,
-                       fixpoint=abi.FP_AC1 if a.fp == "ac1" else abi.FP_WAC1) as s:
+                       fixpoint=abi.FP_KINDS[a.fp]) as s:
         cfg = s.config()
         r = s.solve()
     st = r["stats"]

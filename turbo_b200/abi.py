@@ -15,7 +15,8 @@ OP_ADD, OP_MUL, OP_TDIV, OP_TMOD, OP_MIN, OP_MAX, OP_EQ, OP_LEQ = range(8)
 OP_NAMES = ["ADD", "MUL", "TDIV", "TMOD", "MIN", "MAX", "EQ", "LEQ"]
 VAR_INPUT_ORDER, VAR_FIRST_FAIL, VAR_ANTI_FIRST_FAIL, VAR_SMALLEST, VAR_LARGEST = range(5)
 VAL_MIN, VAL_MAX, VAL_SPLIT, VAL_REVERSE_SPLIT = range(4)
-FP_AC1, FP_WAC1 = 0, 1
+FP_AC1, FP_WAC1, FP_AC1_ACTIVE, FP_WAC1_ACTIVE = 0, 1, 2, 3
+FP_KINDS = {"ac1": FP_AC1, "wac1": FP_WAC1, "ac1_active": FP_AC1_ACTIVE, "wac1_active": FP_WAC1_ACTIVE}
 MEM_AUTO, MEM_GLOBAL, MEM_STORE_SHARED, MEM_TCN_SHARED, MEM_STORE_CLUSTER = -1, 0, 1, 2, 3
 MEM_NAMES = {0: "global", 1: "store_shared", 2: "tcn_shared", 3: "store_cluster"}
 NUM_TIMERS = 11

@@ -101,6 +101,7 @@ struct Ctl {                       // per-CTA control block in static shared mem
   int remaining_depth, depth, cur_strategy, next_unassigned, snap_strategy, snap_next_unassigned;
   int best_bound;
   int pushed;
+  int dirty_all;                   // active-set fixpoint: the store was rewritten, every chunk must be evaluated
   long long t_mark;
 };
 
@@ -215,7 +216,7 @@ __device__ __forceinline__ void decode_word(unsigned long long w, int& a, int& b
   if (!tbd::cls_loads_z(CLS)) c = (c << (32 - TBC_FIELD_BITS)) >> (32 - TBC_FIELD_BITS);
 }
 
-template <int MEM>
+template <int MEM, bool ACT = false>
 struct Ctx {
   const DevParams& P;
   Ctl& c;
@@ -249,6 +250,7 @@ struct Ctx {
   // CTA moves its own slice with its own mbarrier.
   __device__ __forceinline__ void load_store(const int* gsrc) {
     sync();
+    if (ACT && threadIdx.x == 0) c.dirty_all = 1;       // (read after the next barrier, at the start of a fixpoint)
     if (MEM == TB_MEM_GLOBAL) {
       const unsigned bytes = (unsigned)P.vpad * 8u;
       const int4* s4 = (const int4*)gsrc; int4* d4 = (int4*)(MEM == TB_MEM_GLOBAL ? (void*)P.block_store + (size_t)slot * 8 * P.vpad : (void*)sdyn);
@@ -441,6 +443,158 @@ struct Ctx {
     return f;
   }
 
+  // ---- active-set fixpoint (TB_FP_*_ACTIVE; SURVEY 8f.2, the idea of FixpointSubsetGPU, barebones :636,984) ------
+  // Same sweeps, same warp-local WAC1 iteration, same flags as fixpoint(), but a warp only evaluates the chunks one
+  // of whose variables moved since the chunk was last evaluated.  State in dynamic shared memory (P.act_off):
+  //   vbits  : one bit per slot, set (red.or) by whoever moves a bound of the slot;
+  //   dirty  : one byte per chunk, grouped per owning warp (chunk ch = flag ch / nwarps of warp ch % nwarps), set in
+  //            the marking phase between two sweeps from vbits and the slot -> chunks watch lists (global, L2), cleared
+  //            by the owning warp when it evaluates the chunk;
+  //   notent : one byte per chunk, the fused `ask` of its last evaluation (valid while the chunk is clean).
+  // Markers only write `dirty` between the two barriers of the marking phase and owners only during a sweep, so the
+  // flags need no atomics.  A chunk that is clean has seen no change since it was found at its local fixpoint, so a
+  // sweep that publishes nothing ends at the same greatest fixpoint as the dense sweeps.
+  __device__ __forceinline__ unsigned* act_vbits() const { return (unsigned*)(sdyn + P.act_off); }
+
+  // A bound of `slot` was moved outside the fixpoint (decision, incumbent): its watchers are due.
+  __device__ __forceinline__ void mark_var(int slot) const {
+    if (ACT) atomicOr(act_vbits() + (slot >> 5), 1u << (slot & 31));
+  }
+
+  template <int CLS>
+  __device__ __forceinline__ void active_visit(Hot& h, const Words& cur, const bool wac1, const int ch, unsigned* vbits,
+                                               unsigned char* ne_slot, unsigned& evals, unsigned& pad_evals, int& late_chg, int& failed) {
+    const StoreRef<MEM>& store = h.store;
+    int fa[TBC_U], fb[TBC_U], fc[TBC_U];
+#pragma unroll
+    for (int u = 0; u < TBC_U; ++u) decode_word<CLS>(cur.w[u], fa[u], fb[u], fc[u]);
+    tbd::Snap s[TBC_U];
+    const unsigned e0 = evals;
+    bool dead = false;
+    for (;;) {
+      bool chg = false;
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) chg |= tbd::has_work<CLS>(s[u]);
+      ++evals;
+      if (!__any_sync(0xffffffffu, chg)) break;
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) {
+        tbd::Snap n;
+        tbd::narrow<CLS>(s[u], n);
+        tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], n, h.narrowed);
+        if (tbd::cls_loads_x(CLS) && ((n.xl != s[u].xl) | (n.xu != s[u].xu))) atomicOr(vbits + (fa[u] >> 5), 1u << (fa[u] & 31));
+        if ((n.yl != s[u].yl) | (n.yu != s[u].yu)) atomicOr(vbits + (fb[u] >> 5), 1u << (fb[u] & 31));
+        if (tbd::cls_loads_z(CLS) && ((n.zl != s[u].zl) | (n.zu != s[u].zu))) atomicOr(vbits + (fc[u] >> 5), 1u << (fc[u] & 31));
+      }
+      bool fail = false;
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) fail |= tbd::emptied<CLS>(store, fa[u], fb[u], fc[u]);
+      dead = __any_sync(0xffffffffu, fail);
+      if (dead | !wac1) { late_chg = 1; break; }
+    }
+    int ne = 0;
+#pragma unroll
+    for (int u = 0; u < TBC_U; ++u) ne |= tbd::not_entailed_bits<CLS>(s[u]);
+    const bool any_ne = __any_sync(0xffffffffu, ne != 0);
+    if ((tid & 31) == 0) *ne_slot = any_ne ? 1 : 0;
+    if (dead) failed = 1;
+    if (ch == P.cls_begin[CLS + 1] - 1) pad_evals += (evals - e0) * (unsigned)(32 * TBC_U - P.cls_last[CLS]);
+  }
+
+  __device__ __forceinline__ int fixpoint_active(int& iters) {
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = T >> 5;
+    const int lw = 31 - __clz(nwarps);
+    const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
+    unsigned* vbits = act_vbits();
+    const int nvw = P.vpad >> 5, FPW = P.act_fpw;
+    unsigned char* dirty = (unsigned char*)(vbits + nvw);
+    unsigned char* mydirty = dirty + warp * FPW;
+    unsigned char* mynotent = dirty + nwarps * FPW + warp * FPW;
+    Hot h;
+    h.store = store; h.words = words; h.narrowed = narrowed;
+    unsigned long long ded = 0;
+    int it = 0, f;
+    for (;; ++it) {
+      // ---- marking phase: moved slots -> dirty chunks
+      if (c.dirty_all) {
+        for (int i = tid; i < nwarps * FPW; i += T) { const int w = i / FPW, k = i - w * FPW; dirty[i] = (k * nwarps + w) < P.nchunks ? 1 : 0; }
+        for (int i = tid; i < nvw; i += T) vbits[i] = 0;
+      } else {
+        // warp-cooperative: a warp takes 32 words at a time; for every non-zero word, lane l follows the watch list of
+        // slot 32 * word + l, so the L2 round trips of up to 32 moved slots overlap instead of queueing in one thread
+        for (int base = warp * 32; base < nvw; base += nwarps * 32) {
+          const int i = base + lane;
+          unsigned m = i < nvw ? vbits[i] : 0u;
+          if (m) vbits[i] = 0;
+          unsigned nz = __ballot_sync(0xffffffffu, m != 0u);
+          while (nz) {
+            const int src = __ffs((int)nz) - 1;
+            nz &= nz - 1;
+            const unsigned mw = __shfl_sync(0xffffffffu, m, src);
+            if ((mw >> lane) & 1u) {
+              const int v = ((base + src) << 5) + lane;
+              const int e = __ldg(P.watch_off + v + 1);
+              for (int k = __ldg(P.watch_off + v); k < e; ++k) {
+                const int ch = __ldg(P.watch_list + k);
+                dirty[(ch & (nwarps - 1)) * FPW + (ch >> lw)] = 1;
+              }
+            }
+          }
+        }
+      }
+      sync();
+      if (tid == 0) { c.dirty_all = 0; c.flags[(it + 1) % 3] = 0; }
+      // ---- sweep: this warp's dirty chunks
+      unsigned evals = 0, pad_evals = 0, visits = 0;
+      int late_chg = 0, failed = 0;
+      for (int g = 0; g < FPW && !failed; g += 32) {
+        unsigned mask = __ballot_sync(0xffffffffu, mydirty[g + lane] != 0);
+        if (mask) mydirty[g + lane] = 0;
+        while (mask && !failed) {
+          const int k = g + __ffs((int)mask) - 1;
+          mask &= mask - 1;
+          const int ch = k * nwarps + warp;
+          const Words cur = load_words(h.words, (ch * 32 + lane) * TBC_U);
+          int cls = 0;                                          // warp-uniform; the table is sorted by class:
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1)            // largest cls with cls_begin[cls] <= ch (empty classes skipped by <=)
+            if (cls + step < TBC_NUM && ch >= P.cls_begin[cls + step]) cls += step;
+          switch (cls) {
+#define TB_CASE(CLS) case CLS: active_visit<CLS>(h, cur, wac1, ch, vbits, mynotent + k, evals, pad_evals, late_chg, failed); break;
+            TB_CASE(TBC_ADD_S) TB_CASE(TBC_ADD_XK) TB_CASE(TBC_ADD_ZK) TB_CASE(TBC_ADD_G)
+            TB_CASE(TBC_MUL) TB_CASE(TBC_TDIV) TB_CASE(TBC_TMOD) TB_CASE(TBC_MIN) TB_CASE(TBC_MAX)
+            TB_CASE(TBC_EQ_S) TB_CASE(TBC_EQ_T) TB_CASE(TBC_EQ_F) TB_CASE(TBC_EQ_ZK) TB_CASE(TBC_EQ_G)
+            TB_CASE(TBC_LEQ_S) TB_CASE(TBC_LEQ_T) TB_CASE(TBC_LEQ_F) TB_CASE(TBC_LEQ_ZK) TB_CASE(TBC_LEQ_G)
+#undef TB_CASE
+            default: break;
+          }
+          ++visits;
+        }
+      }
+      __syncwarp();
+      int ne = 0;
+      for (int g = 0; g < FPW; g += 32) ne |= mynotent[g + lane];
+      ded += (unsigned long long)evals * (unsigned long long)(32 * TBC_U) - (unsigned long long)pad_evals;
+      const bool changed = evals > visits || late_chg;
+      int bits = (changed ? F_CHANGED : 0) | (failed ? F_FAILED : 0) | (ne ? F_NOT_ENTAILED : 0);
+      bits = __reduce_or_sync(0xffffffffu, bits);
+      const int slot = it % 3;
+      if (lane == 0 && bits) atomicOr(&c.flags[slot], bits);
+      sync();
+      f = c.flags[slot];
+      if (!(f & F_CHANGED) || (f & F_FAILED)) break;
+    }
+    iters = it + 1;
+    narrowed = h.narrowed;
+    deductions += ded;
+    sync();
+    if (tid < 3) c.flags[tid] = 0;
+    sync();
+    return f;
+  }
+
   // ---- propagate() (barebones :903-1031) -----------------------------------------------------------
   // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
   // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
@@ -451,7 +605,7 @@ struct Ctx {
     bool pre_failed = P.root_failed != 0;       // a referenced variable is already empty in the root store
     if (P.obj_var >= 0) { int l, u; store.ld(P.obj_var, l, u); pre_failed |= l > u; }
     if (pre_failed) f = F_FAILED;
-    else f = fixpoint(iters);
+    else f = ACT ? fixpoint_active(iters) : fixpoint(iters);
     const bool failed = (f & F_FAILED) != 0;
     const bool solution = !failed && !(f & F_NOT_ENTAILED);
     unsigned long long t1 = 0;
@@ -604,6 +758,7 @@ struct Ctx {
             const Decision& d = dec[0];
             int bit = (int)((idx >> c.remaining_depth) & 1ull);
             store.embed(d.var, bit ? d.clb1 : d.clb0, bit ? d.cub1 : d.cub0);
+            mark_var(d.var);
           }
         }
       }
@@ -668,8 +823,9 @@ struct Ctx {
           if (tid == 0 && P.obj_var >= 0) {
             int appx = *(volatile int*)P.appx_best_bound;
             if (appx != TBD_PINF) {
-              store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
-              store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
+              bool moved = store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
+              moved |= store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
+              if (moved) mark_var(P.obj_var);
             }
             if (appx == TBD_NINF) { c.stop = 1; *P.stop = 1; }
           }
@@ -705,6 +861,7 @@ struct Ctx {
               const Decision& d = dec[0];
               int bit = (int)((idx >> c.remaining_depth) & 1ull);
               store.embed(d.var, bit ? d.clb1 : d.clb0, bit ? d.cub1 : d.cub0);
+            mark_var(d.var);
             }
           }
         }
@@ -724,6 +881,7 @@ struct Ctx {
               Decision& d = dec[c.depth - 1];
               d.cur = 0;
               store.embed(d.var, d.clb0, d.cub0);
+              mark_var(d.var);
             }
           }
           sync();
@@ -767,8 +925,8 @@ __device__ __forceinline__ Ctl* shared_ctl(Ctl* local) {
   return (Ctl*)r;
 }
 
-template <int MEM>
-__device__ __forceinline__ void ctx_init(Ctx<MEM>& k, Ctl* local, unsigned char* dyn) {
+template <int MEM, bool ACT>
+__device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned char* dyn) {
   const DevParams& P = k.P;
   k.lc = local;
   if (MEM == TB_MEM_STORE_CLUSTER) {
@@ -800,7 +958,14 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM>& k, Ctl* local, unsigned char*
     local->stop = 0; local->leaf = 0; local->failed = 0; local->depth = 0; local->pushed = 0;
     local->cur_strategy = 0; local->next_unassigned = 0; local->snap_strategy = 0; local->snap_next_unassigned = 0;
     local->best_bound = TBD_PINF; local->remaining_depth = 0;
+    local->dirty_all = 1;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (ACT) {
+    // vbits, dirty and notent flags start clear; the first fixpoint evaluates everything (dirty_all)
+    const int words_ = (P.vpad >> 5) + ((2 * (int)(blockDim.x >> 5) * P.act_fpw + 3) >> 2);
+    unsigned* a = (unsigned*)(dyn + P.act_off);
+    for (int i = threadIdx.x; i < words_; i += blockDim.x) a[i] = 0u;
   }
   k.sync();
   if (MEM == TB_MEM_TCN_SHARED) {
@@ -818,8 +983,8 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM>& k, Ctl* local, unsigned char*
   }
 }
 
-template <int MEM>
-__device__ __forceinline__ void ctx_finish(Ctx<MEM>& k) {
+template <int MEM, bool ACT>
+__device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
   // fold the per-thread / per-warp counters into the block statistics
   unsigned n = k.narrowed;
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -835,12 +1000,12 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM>& k) {
 // ================================================================================================
 
 // The persistent dive-and-solve kernel (gpu_barebones_solve, barebones :620-901).
-template <int MEM>
+template <int MEM, bool ACT = false>
 __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_constant__ DevParams P) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM> k(P, c);
+  Ctx<MEM, ACT> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid;
   BlockStats* st = k.st;
@@ -855,14 +1020,14 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
 }
 
 // One fixpoint per block on caller-provided stores (tb_propagate / tb_propagate_batch).
-template <int MEM>
+template <int MEM, bool ACT = false>
 __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_constant__ DevParams P, int nstores,
                                                          const int* in_lb, const int* in_ub,
                                                          int* out_lb, int* out_ub, int* out_failed, int repeat) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM> k(P, c);
+  Ctx<MEM, ACT> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid, T = k.T;
   for (int s = k.slot; s < nstores; s += k.nslots) {
@@ -871,7 +1036,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_
       k.sync();
       // load the caller's store into the block store (slot order); a referenced variable that is already
       // empty fails the store before any propagation, as the oracle's deduce does
-      if (tid == 0) c.leaf = 0;
+      if (tid == 0) { c.leaf = 0; c.dirty_all = 1; }
       k.sync();
       int empty_seen = 0;
       if (P.vpad != P.nvars) {                 // padding slots hold the singleton 0
@@ -885,7 +1050,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_
       if (empty_seen) atomicOr(&c.leaf, 1);
       k.sync();
       if (c.leaf) { f = F_FAILED; iters = 0; k.sync(); }
-      else f = k.fixpoint(iters);
+      else f = ACT ? k.fixpoint_active(iters) : k.fixpoint(iters);
       if (tid == 0) {
         k.st->fixpoint_iterations += (unsigned long long)iters;
         k.st->nodes++;
@@ -902,13 +1067,13 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_
 }
 
 // EPS dive only (tb_dive / tb_dive_batch).
-template <int MEM>
+template <int MEM, bool ACT = false>
 __global__ void __launch_bounds__(TB_MAX_THREADS) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
                                                     int depth, int* out_lb, int* out_ub, int* out_remaining, int* out_kind) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM> k(P, c);
+  Ctx<MEM, ACT> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid, T = k.T;
   for (int s = k.slot; s < count; s += k.nslots) {
@@ -961,6 +1126,7 @@ struct tb_solver {
   TnfLayout layout;                   // device table + variable placement (layout.h)
   std::vector<int32_t> root_lb, root_ub;   // the root domains (precondition check of tb_propagate)
   size_t shared_bytes = 0, store_bytes = 0, prop_bytes = 0;
+  bool want_active = false, active = false;   // TB_FP_*_ACTIVE requested / in effect (shared-memory placements)
   int num_sms = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -1019,11 +1185,15 @@ static int32_t* pinned_one() {
 // kernel dispatch over the placement
 template <class F>
 static tb_status dispatch(const tb_solver* s, F&& f) {
+  using Dense = std::false_type;
+  using Active = std::true_type;          // active-set fixpoint: shared-memory placements only
   switch (s->mem_kind) {
-    case TB_MEM_GLOBAL: return f(std::integral_constant<int, TB_MEM_GLOBAL>{});
-    case TB_MEM_STORE_SHARED: return f(std::integral_constant<int, TB_MEM_STORE_SHARED>{});
-    case TB_MEM_TCN_SHARED: return f(std::integral_constant<int, TB_MEM_TCN_SHARED>{});
-    case TB_MEM_STORE_CLUSTER: return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{});
+    case TB_MEM_GLOBAL: return f(std::integral_constant<int, TB_MEM_GLOBAL>{}, Dense{});
+    case TB_MEM_STORE_SHARED:
+      return s->active ? f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Active{}) : f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{});
+    case TB_MEM_TCN_SHARED:
+      return s->active ? f(std::integral_constant<int, TB_MEM_TCN_SHARED>{}, Active{}) : f(std::integral_constant<int, TB_MEM_TCN_SHARED>{}, Dense{});
+    case TB_MEM_STORE_CLUSTER: return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, Dense{});
     default: break;
   }
   set_error("unsupported memory kind");
@@ -1068,7 +1238,10 @@ static tb_status configure(tb_solver* s) {
   const size_t max_block_smem = dp.sharedMemPerBlockOptin;               // 227 KB on sm_100
   const size_t sm_smem = dp.sharedMemPerMultiprocessor;                  // 228 KB
   const size_t reserved = dp.reservedSharedMemPerBlock + sizeof(Ctl) + 64;
-  const size_t store_b = s->store_bytes, prop_b = s->prop_bytes;
+  // the active-set fixpoint keeps one bit per slot and two bytes per chunk next to the store (upper bound here, the
+  // exact figure needs the thread count: place_active)
+  const size_t act_b = s->want_active ? (s->store_bytes / 64 + 2 * ((size_t)s->P.nchunks + 1024) + 64) : 0;
+  const size_t store_b = s->store_bytes + act_b, prop_b = s->prop_bytes;
   auto blocks_for = [&](size_t dyn) -> int {
     if (dyn + sizeof(Ctl) + 64 > max_block_smem) return 0;
     return (int)std::min<size_t>(32, sm_smem / (dyn + reserved));
@@ -1141,19 +1314,35 @@ static tb_status configure(tb_solver* s) {
   return TB_OK;
 }
 
+// Active-set fixpoint: exact size and position of its flags once the layout pass has fixed the store image and the
+// placement policy the thread count.  Shared-memory placements only; elsewhere the plain sweeps run.
+static void place_active(tb_solver* s) {
+  s->active = s->want_active && (s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED);
+  s->P.act_off = 0; s->P.act_fpw = 0;
+  if (!s->active) return;
+  const int nwarps = s->threads / 32;
+  const int per_warp = (s->P.nchunks + nwarps - 1) / nwarps;
+  s->P.act_fpw = std::max(32, (per_warp + 31) / 32 * 32);
+  const size_t table = s->mem_kind == TB_MEM_TCN_SHARED ? (size_t)s->P.nchunks * 32 * TBC_U * 8 : 0;
+  s->P.act_off = (int)(s->store_bytes + table);
+  const size_t act = (size_t)s->P.vpad / 8 + (size_t)2 * nwarps * s->P.act_fpw;
+  s->shared_bytes = (size_t)s->P.act_off + (act + 15) / 16 * 16;
+}
+
 static tb_status set_smem_attr(tb_solver* s) {
-  return dispatch(s, [&](auto M) -> tb_status {
+  return dispatch(s, [&](auto M, auto A) -> tb_status {
     constexpr int m = decltype(M)::value;
+    constexpr bool act = decltype(A)::value;
     if (s->shared_bytes) {
-      CU(cudaFuncSetAttribute(solve_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
-      CU(cudaFuncSetAttribute(propagate_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
-      CU(cudaFuncSetAttribute(dive_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(solve_kernel<m, act>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(propagate_kernel<m, act>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(dive_kernel<m, act>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
     }
     if (m == TB_MEM_STORE_CLUSTER) {
       if (s->cluster > 8) {
-        CU(cudaFuncSetAttribute(solve_kernel<m>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU(cudaFuncSetAttribute(propagate_kernel<m>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU(cudaFuncSetAttribute(dive_kernel<m>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(solve_kernel<m, act>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(propagate_kernel<m, act>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(dive_kernel<m, act>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       }
       cudaLaunchConfig_t cfg = {};
       cfg.blockDim = dim3((unsigned)s->threads);
@@ -1164,7 +1353,7 @@ static tb_status set_smem_attr(tb_solver* s) {
       attr[0].val.clusterDim.x = (unsigned)s->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int nclusters = 0;
-      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m>, &cfg));
+      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m, act>, &cfg));
       if (nclusters < 1) { set_error("the device cannot host a cluster of this size"); return TB_ERR_UNSUPPORTED; }
       int workers = nclusters;
       if (s->opt.or_blocks > 0) workers = std::min(workers, s->opt.or_blocks);
@@ -1172,7 +1361,7 @@ static tb_status set_smem_attr(tb_solver* s) {
     } else {
       // registers limit the resident CTAs too: ask the driver what really fits (persistent kernel: one wave)
       int per_sm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<m>, s->threads, s->shared_bytes));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<m, act>, s->threads, s->shared_bytes));
       if (per_sm < 1) { set_error("the solve kernel does not fit on an SM with this configuration"); return TB_ERR_UNSUPPORTED; }
       if (per_sm < s->blocks_per_sm) {
         s->blocks_per_sm = per_sm;
@@ -1242,7 +1431,8 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   P.nvars = pb->nvars; P.nprops = pb->nprops;
   P.obj_var = pb->obj_var;
   P.has_eps_strategy = pb->has_eps_strategy;
-  P.fixpoint_kind = opt.fixpoint == TB_FP_AC1 ? TB_FP_AC1 : TB_FP_WAC1;
+  P.fixpoint_kind = (opt.fixpoint == TB_FP_AC1 || opt.fixpoint == TB_FP_AC1_ACTIVE) ? TB_FP_AC1 : TB_FP_WAC1;
+  s->want_active = opt.fixpoint == TB_FP_AC1_ACTIVE || opt.fixpoint == TB_FP_WAC1_ACTIVE;
   P.wac1_threshold = opt.wac1_threshold;
   P.cutnodes = opt.cutnodes;
   P.rank = opt.gpu_rank; P.world = opt.gpu_world;
@@ -1280,6 +1470,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (pb->obj_var >= 0) P.obj_var = L.slot_of[pb->obj_var];
     for (int v = 0; v < pb->nvars; ++v) if (L.referenced[v] && pb->lb[v] > pb->ub[v]) P.root_failed = 1;
   }
+  place_active(s);
   if ((rc = set_smem_attr(s)) != TB_OK) return fail(rc);
 
   // ---- device images ---------------------------------------------------------------------------------
@@ -1299,6 +1490,14 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (cudaMemset(d, 0, (L.words.size() + 64 * 32 * TBC_U) * 8) != cudaSuccess ||
         (L.words.size() && cudaMemcpy(d, L.words.data(), L.words.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
     P.words = d;
+    if (s->active) {
+      int *wo = nullptr, *wl = nullptr;
+      if ((rc = dev_alloc(s, &wo, L.watch_off.size()))) return fail(rc);
+      if ((rc = dev_alloc(s, &wl, std::max<size_t>(1, L.watch_list.size())))) return fail(rc);
+      if (cudaMemcpy(wo, L.watch_off.data(), L.watch_off.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+          (L.watch_list.size() && cudaMemcpy(wl, L.watch_list.data(), L.watch_list.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D watch lists"); return fail(TB_ERR_CUDA); }
+      P.watch_off = wo; P.watch_list = wl;
+    }
     std::vector<int> var_of((size_t)P.vpad, -1);
     for (int v = 0; v < pb->nvars; ++v) var_of[L.slot_of[v]] = v;
     int *dslot = nullptr, *dvar = nullptr;
@@ -1478,8 +1677,8 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   CU(cudaMemcpyAsync(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
   CU(cudaMemcpyAsync(s->d_next, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
-  rc = dispatch(s, [&](auto M) -> tb_status {
-    CU(launch_workers(s, solve_kernel<decltype(M)::value>, s->num_blocks, P));
+  rc = dispatch(s, [&](auto M, auto A) -> tb_status {
+    CU(launch_workers(s, solve_kernel<decltype(M)::value, decltype(A)::value>, s->num_blocks, P));
     CU(cudaGetLastError());
     return TB_OK;
   });
@@ -1574,8 +1773,8 @@ extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int
   }
   const int repeat = std::max(1, s->opt.propagate_repeat);
   CU(cudaEventRecord(s->ev_start, s->stream));
-  rc = dispatch(s, [&](auto M) -> tb_status {
-    CU(launch_workers(s, propagate_kernel<decltype(M)::value>, grid, s->P, nstores,
+  rc = dispatch(s, [&](auto M, auto A) -> tb_status {
+    CU(launch_workers(s, propagate_kernel<decltype(M)::value, decltype(A)::value>, grid, s->P, nstores,
                       (const int*)s->d_in_lb, (const int*)s->d_in_ub, s->d_out_lb, s->d_out_ub, s->d_out_i0, repeat));
     CU(cudaGetLastError());
     return TB_OK;
@@ -1621,8 +1820,8 @@ extern "C" tb_status tb_dive_batch(tb_solver* s, uint64_t first, int32_t count, 
   DevParams P = s->P;
   P.cutnodes = 0;
   P.t_start = 0;
-  rc = dispatch(s, [&](auto M) -> tb_status {
-    CU(launch_workers(s, dive_kernel<decltype(M)::value>, grid, P,
+  rc = dispatch(s, [&](auto M, auto A) -> tb_status {
+    CU(launch_workers(s, dive_kernel<decltype(M)::value, decltype(A)::value>, grid, P,
                       (unsigned long long)first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1));
     CU(cudaGetLastError());
     return TB_OK;

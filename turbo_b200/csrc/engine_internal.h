@@ -53,4 +53,9 @@ struct DevParams {
   int* appx_best_bound;                  // GridData::appx_best_bound (:426), this GPU's copy
   int* const* peer_bounds;               // the other GPUs' copies (peer-mapped over NVLink)
   volatile int* stop;                    // UnifiedData::stop (:64), raised by the host with an async copy
+  // active-set fixpoint (TB_FP_*_ACTIVE): slot -> chunks that load it (CSR), and where its flags live in shared memory
+  const int* watch_off;                  // vpad + 1 offsets into watch_list
+  const int* watch_list;                 // chunk ids, ascending per slot
+  int act_off;                           // byte offset of the active-set area in dynamic shared memory
+  int act_fpw;                           // chunk flags per warp (multiple of 32): chunk ch is flag (ch / nwarps) of warp (ch % nwarps)
 };

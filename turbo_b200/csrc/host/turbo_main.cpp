@@ -37,7 +37,7 @@ struct Config {                      // Configuration<> (include/config.hpp:32-5
 
 void usage_and_exit(const std::string& prog) {
   std::cout << "usage: " << prog << " [-t 2000] [-a] [-n 10] [-i] [-f] [-s] [-v] [-p <i>] [-arch <barebones|gpu|hybrid>] [-or 48] [-sub 12] "
-               "[-subfactor 300] [-stack 100] [-fp <ac1|wac1>] [-wac1_threshold 0] [-eps_var_order <input_order|first_fail|anti_first_fail|smallest|largest>] "
+               "[-subfactor 300] [-stack 100] [-fp <ac1|wac1|ac1_active|wac1_active>] [-wac1_threshold 0] [-eps_var_order <input_order|first_fail|anti_first_fail|smallest|largest>] "
                "[-eps_value_order <min|max|split|reverse_split>] [-seed 0] [-cutnodes 0] [-disable_simplify] [-force_ternarize] [-globalmem] "
                "[-disable_network_analysis] [-version 1.0.0] [-hardware <desc>] [-gpus 1] [-tpb 0] fzninstance.fzn|instance.tnf" << std::endl;
   std::cout << "\t-t 2000: Run the solver with a timeout of 2000 milliseconds (-timeout overrides -t)." << std::endl;
@@ -48,7 +48,7 @@ void usage_and_exit(const std::string& prog) {
   std::cout << "\t-v: Print log messages; repeat for more." << std::endl;
   std::cout << "\t-p 48 / -or 48: number of thread blocks searching in parallel (0 = automatic)." << std::endl;
   std::cout << "\t-arch: barebones is the only GPU architecture; gpu and hybrid are mapped onto it. cpu is not available in this build." << std::endl;
-  std::cout << "\t-fp <ac1|wac1>: fixpoint strategy (default wac1)." << std::endl;
+  std::cout << "\t-fp <ac1|wac1|ac1_active|wac1_active>: fixpoint strategy (default wac1); the _active kinds only re-evaluate propagators whose variables changed." << std::endl;
   std::cout << "\t-sub 12: create 2^12 subproblems (-1: at least subfactor * blocks * gpus)." << std::endl;
   std::cout << "\t-cutnodes 1000: stop a block after 1000 nodes (0 for no limit)." << std::endl;
   std::cout << "\t-globalmem: keep the variable store in global memory." << std::endl;
@@ -116,7 +116,7 @@ Config parse_args(int argc, char** argv) {
   }
   std::string fp;
   if (in.read_string("-fp", fp)) {
-    if (fp != "ac1" && fp != "wac1") { std::cerr << "Unknown fixpoint -fp " << fp << std::endl; exit(EXIT_FAILURE); }
+    if (fp != "ac1" && fp != "wac1" && fp != "ac1_active" && fp != "wac1_active") { std::cerr << "Unknown fixpoint -fp " << fp << std::endl; exit(EXIT_FAILURE); }
     c.fixpoint = fp;
   }
   in.read_size("-wac1_threshold", c.wac1_threshold);
@@ -146,7 +146,7 @@ void print_commandline(const Config& c, const char* prog) {      // config.hpp:1
   if (c.force_ternarize) printf("-force_ternarize ");
   if (c.disable_network_analysis) printf("-disable_network_analysis ");
   printf("-fp %s ", c.fixpoint.c_str());
-  if (c.fixpoint == "wac1") printf("-wac1_threshold %zu ", c.wac1_threshold);
+  if (c.fixpoint == "wac1" || c.fixpoint == "wac1_active") printf("-wac1_threshold %zu ", c.wac1_threshold);
   printf("-seed %zu -eps_var_order %s -eps_value_order %s ", c.seed, c.eps_var_order.c_str(), c.eps_value_order.c_str());
   if (!c.version.empty()) printf("-version %s ", c.version.c_str());
   if (!c.hardware.empty()) printf("-hardware '%s' ", c.hardware.c_str());
@@ -214,7 +214,7 @@ void print_config_stats(const Config& c, const tb_stats& st) {       // config.h
   printf("%%%%%%mzn-stat: arch=\"%s\"\n", "barebones");
   printf("%%%%%%mzn-stat: fixpoint=\"%s\"\n", c.fixpoint.c_str());
   printf("%%%%%%mzn-stat: subproblems_factor=%zu\n", c.subproblems_factor);
-  if (c.fixpoint == "wac1") printf("%%%%%%mzn-stat: wac1_threshold=%zu\n", c.wac1_threshold);
+  if (c.fixpoint == "wac1" || c.fixpoint == "wac1_active") printf("%%%%%%mzn-stat: wac1_threshold=%zu\n", c.wac1_threshold);
   printf("%%%%%%mzn-stat: seed=%zu\n", c.seed);
   printf("%%%%%%mzn-stat: eps_var_order=\"%s\"\n", c.eps_var_order.c_str());
   printf("%%%%%%mzn-stat: eps_value_order=\"%s\"\n", c.eps_value_order.c_str());
@@ -369,7 +369,7 @@ int main(int argc, char** argv) {
   for (int g = 0; g < G; ++g) {
     tb_options o;
     memset(&o, 0, sizeof(o));
-    o.fixpoint = config.fixpoint == "ac1" ? TB_FP_AC1 : TB_FP_WAC1;
+    o.fixpoint = config.fixpoint == "ac1" ? TB_FP_AC1 : config.fixpoint == "ac1_active" ? TB_FP_AC1_ACTIVE : config.fixpoint == "wac1_active" ? TB_FP_WAC1_ACTIVE : TB_FP_WAC1;
     o.wac1_threshold = (int32_t)config.wac1_threshold;
     o.subproblems_power = config.subproblems_power;
     o.subproblems_factor = (int32_t)config.subproblems_factor;

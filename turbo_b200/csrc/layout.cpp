@@ -219,6 +219,30 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
     last_word = f0 | (f1 << TBC_FIELD_BITS) | (f2 << (2 * TBC_FIELD_BITS));
     L.words[dst] = last_word;
   }
+
+  // ---- watch lists: which chunks load a slot (the active-set fixpoint re-evaluates exactly those when it moves) ----
+  {
+    std::vector<std::vector<int>> w((size_t)L.nslots);
+    for (size_t i = 0; i < lanes.size(); ++i) {
+      if (lanes[i] < 0) continue;
+      const int ch = (int)(i / 32 / TBC_U);
+      const Item& it = items[lanes[i]];
+      auto add = [&](int var) { std::vector<int>& l = w[(size_t)L.slot_of[var]]; if (l.empty() || l.back() != ch) l.push_back(ch); };
+      if (loads_x(it.cls)) add(it.x);
+      add(it.y);
+      if (loads_z(it.cls)) add(it.z);
+    }
+    L.watch_off.assign((size_t)L.nslots + 1, 0);
+    L.watch_list.clear();
+    for (int sl = 0; sl < L.nslots; ++sl) {
+      std::vector<int>& l = w[(size_t)sl];
+      std::sort(l.begin(), l.end());
+      l.erase(std::unique(l.begin(), l.end()), l.end());
+      L.watch_off[(size_t)sl] = (int)L.watch_list.size();
+      L.watch_list.insert(L.watch_list.end(), l.begin(), l.end());
+    }
+    L.watch_off[(size_t)L.nslots] = (int)L.watch_list.size();
+  }
   return TB_OK;
 }
 

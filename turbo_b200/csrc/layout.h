@@ -25,6 +25,7 @@ struct TnfLayout {
   uint64_t loads_per_sweep = 0;            // 8-byte {lb, ub} loads one sweep over the table issues (real lanes)
   double wavefronts_per_load = 0.0;        // bank model: average shared-memory wavefronts per half-warp load
   bool identity = true;                    // slot_of[v] == v
+  std::vector<int> watch_off, watch_list;  // slot -> chunks that load it (CSR over nslots; active-set fixpoint)
 };
 
 struct TnfLayoutOptions {
