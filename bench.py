@@ -158,7 +158,19 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator is created (NCCL_DEBUG=VERSION and up):
+        # create it with stdout pointing at stderr, so that rank 0's stdout carries the one JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     pb, info = load_workload(args.workload)
     opts = dict(device=local, gpu_rank=rank, gpu_world=world, cutnodes=args.cutnodes,
