@@ -1,0 +1,36 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out
+( time timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_active.py tests/test_known_answers.py tests/test_multi_gpu.py -m gpu -x -q ) > $O/pytest_snap.log 2>&1
+tail -5 $O/pytest_snap.log
+B="python bench.py --no-cpu-baseline --no-fixpoint-leg"
+run() { echo "== $*" >> $O/exp11.log; timeout 300 "$@" >> $O/exp11.log 2>> $O/exp11.err; }
+for w in simplified:trains15 trains15 simplified:example_wordpress7_500 simplified:accap_a3; do
+  run env TB_SNAPSHOT_MB=0 $B --workload $w
+  run $B --workload $w
+done
+python - <<'PY'
+import json, sys
+sys.path.insert(0, ".")
+for line in open("gpurun_out/exp11.log"):
+    line = line.strip()
+    if line.startswith("{"):
+        d = json.loads(line)
+        c = d["config"]
+        print("   %s tpb %d blocks %d | Gprop/s %.1f nodes/s %.0f frac %.4f fixpoint share %.2f e2e %.1f" % (
+            c["memory_configuration"], c["threads_per_block"], c["num_blocks_per_gpu"], d["value"] / 1e9, d["nodes_per_sec"], d["roofline"]["frac"], d["fixpoint_time_share"], d["e2e"]["value"] / 1e9))
+    else:
+        print(line)
+from tests import golden_io
+from turbo_b200 import abi, engine
+import os
+pb, info = golden_io.load_simplified_problem("trains15")
+for mb in ("0", "4096"):
+    os.environ["TB_SNAPSHOT_MB"] = mb
+    with engine.Solver(pb, cutnodes=2000) as s:
+        r = s.solve()
+    st = r["stats"]
+    print("snapshot MB", mb, "nodes", st["nodes"], "sweeps/node %.2f" % (st["fixpoint_iterations"] / st["nodes"]), "evals/node %.0f" % (st["num_deductions"] / st["nodes"]),
+          "fails", st["fails"], "kernel_ms %.1f" % st["kernel_ms"], "obj", r["objective"])
+PY
+tail -3 $O/exp11.err

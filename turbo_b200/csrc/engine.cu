@@ -23,6 +23,7 @@
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -227,6 +228,8 @@ struct Ctx {
   unsigned narrowed;       // per-thread count of published bounds
   unsigned long long deductions;     // per-warp (lane-uniform) count of propagator evaluations
   int* g_root;             // this block's snapshot (global, same layout as the store)
+  int* g_snap;             // this block's snapshot ring (P.nsnap images) and its tags
+  int* g_snap_tag;
   int* g_best;
   Decision* dec;
   BlockStats* st;
@@ -792,6 +795,7 @@ struct Ctx {
           c.remaining_depth = P.subproblems_power; c.leaf = 0; c.failed = 0;
           c.t_mark = (long long)globaltimer_ns();
         }
+        for (int i = tid; i < P.nsnap; i += T) g_snap_tag[i] = -1;       // snapshots belong to one subproblem
         load_store(P.root_store);
         sync();
         mode = M_DIVE;
@@ -875,6 +879,13 @@ struct Ctx {
             sync();
           }
           bool pushed = split();
+          if (pushed && P.nsnap) {
+            // copying instead of recomputation: keep this node's fixpoint, so that the right branch of the decision
+            // restarts from here (one changed variable) instead of from the subproblem root plus a replay
+            const int j = c.depth - 1;
+            save_store(g_snap + (size_t)(j % P.nsnap) * 2 * P.vpad);
+            if (tid == 0) g_snap_tag[j % P.nsnap] = j;
+          }
           if (tid == 0) {
             if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
             else {
@@ -894,10 +905,15 @@ struct Ctx {
           sync();
           const int depth = c.depth;
           if (depth == -1) { mode = M_SOLVE_END; continue; }
-          load_store(g_root);
-          for (int i = tid; i < depth - 1; i += T) {
-            const Decision d = dec[i];
-            store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+          // the node where decision depth-1 was taken is in the snapshot ring unless a deeper level has reused its slot
+          const bool snap = P.nsnap && *(volatile int*)(g_snap_tag + (depth - 1) % P.nsnap) == depth - 1;      // uniform (global, written before a barrier)
+          if (snap) load_store(g_snap + (size_t)((depth - 1) % P.nsnap) * 2 * P.vpad);
+          else {
+            load_store(g_root);
+            for (int i = tid; i < depth - 1; i += T) {
+              const Decision d = dec[i];
+              store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+            }
           }
           if (tid == 0) {
             Decision& d = dec[depth - 1];
@@ -949,6 +965,8 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   k.deductions = 0;
   k.g_root = P.block_root + (size_t)slot * 2 * P.vpad;
   k.g_best = P.block_best + (size_t)slot * 2 * P.vpad;
+  k.g_snap = P.nsnap ? P.block_snap + (size_t)slot * P.nsnap * 2 * P.vpad : nullptr;
+  k.g_snap_tag = P.nsnap ? P.snap_tag + (size_t)slot * P.nsnap : nullptr;
   k.dec = P.decisions + (size_t)slot * P.max_depth;
   k.st = P.stats + slot;
   if (threadIdx.x == 0) {
@@ -1175,10 +1193,11 @@ static tb_status dev_alloc(tb_solver* s, T** p, size_t count) {
 // One pinned word holding the constant 1 (source of the asynchronous "stop" copy), shared by all solvers.
 static int32_t* pinned_one() {
   static int32_t* p = nullptr;
-  if (!p) {
+  static std::once_flag once;               // solvers of several GPUs may be created from concurrent host threads
+  std::call_once(once, [] {
     if (cudaHostAlloc((void**)&p, 64, cudaHostAllocPortable) != cudaSuccess) { p = nullptr; cudaGetLastError(); }
     else *p = 1;
-  }
+  });
   return p;
 }
 
@@ -1383,6 +1402,21 @@ static tb_status ensure_scratch(tb_solver* s, int slots) {
   if ((rc = dev_alloc(s, &P.block_best, img * slots))) return rc;
   if (s->mem_kind == TB_MEM_GLOBAL) { if ((rc = dev_alloc(s, &P.block_store, img * slots))) return rc; }
   if ((rc = dev_alloc(s, &P.decisions, (size_t)P.max_depth * slots))) return rc;
+  {
+    // snapshot ring: as many levels as a memory budget allows (TB_SNAPSHOT_MB, default 4096 MB per GPU; 0 disables),
+    // at most 64 per block
+    const size_t budget = (size_t)std::max(0, env_int("TB_SNAPSHOT_MB", 4096)) << 20;
+    const size_t per_level = img * sizeof(int) * (size_t)slots;
+    int n = (int)std::min<size_t>(64, per_level ? budget / per_level : 0);
+    if (s->opt.max_depth > 0) n = std::min(n, s->opt.max_depth);
+    P.nsnap = 0; P.block_snap = nullptr; P.snap_tag = nullptr;
+    if (n >= 2) {
+      if (dev_alloc(s, &P.block_snap, img * (size_t)slots * (size_t)n) == TB_OK && dev_alloc(s, &P.snap_tag, (size_t)slots * (size_t)n) == TB_OK) {
+        if (cudaMemset(P.snap_tag, 0xff, (size_t)slots * (size_t)n * sizeof(int)) != cudaSuccess) { set_error("memset snapshot tags"); return TB_ERR_CUDA; }
+        P.nsnap = n;
+      } else { cudaGetLastError(); P.block_snap = nullptr; P.snap_tag = nullptr; }    // no room: recompute on backtrack as the reference does
+    }
+  }
   if ((rc = dev_alloc(s, &P.stats, (size_t)slots))) return rc;
   s->scratch_blocks = slots;
   return TB_OK;

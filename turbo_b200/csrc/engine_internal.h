@@ -48,6 +48,11 @@ struct DevParams {
   int* block_store;             // current store when it does not live in shared memory
   Decision* decisions;
   BlockStats* stats;
+  // snapshot ring (copying instead of recomputation on backtrack): store image of the node where decision j was taken,
+  // kept in slot j % nsnap of the block; snap_tag says which j a slot holds (-1 = none)
+  int* block_snap;              // [slot][nsnap] images of 2 * vpad ints
+  int* snap_tag;                // [slot][nsnap]
+  int nsnap, pad2_;
   // grid-shared cells
   unsigned long long* next_subproblem;   // GridData::next_subproblem (:418), counts this GPU's shard
   int* appx_best_bound;                  // GridData::appx_best_bound (:426), this GPU's copy

@@ -366,26 +366,37 @@ int main(int argc, char** argv) {
   config.gpus = G;
   std::vector<tb_solver*> solvers((size_t)G, nullptr);
   S.i("subproblems_power", config.subproblems_power);
-  for (int g = 0; g < G; ++g) {
-    tb_options o;
-    memset(&o, 0, sizeof(o));
-    o.fixpoint = config.fixpoint == "ac1" ? TB_FP_AC1 : config.fixpoint == "ac1_active" ? TB_FP_AC1_ACTIVE : config.fixpoint == "wac1_active" ? TB_FP_WAC1_ACTIVE : TB_FP_WAC1;
-    o.wac1_threshold = (int32_t)config.wac1_threshold;
-    o.subproblems_power = config.subproblems_power;
-    o.subproblems_factor = (int32_t)config.subproblems_factor;
-    o.or_blocks = (int32_t)config.or_nodes;
-    o.threads_per_block = config.threads_per_block;
-    o.mem_kind = config.only_global_memory ? TB_MEM_GLOBAL : TB_MEM_AUTO;
-    o.verbose = config.verbose;
-    o.gpu_rank = g; o.gpu_world = G; o.device = g;
-    o.cutnodes = config.stop_after_n_nodes;
-    o.seed = config.seed;
-    if (config.timeout_ms) {
-      int64_t left = (int64_t)config.timeout_ms - since_ns() / 1000000;
-      o.timeout_ms = (uint64_t)std::max<int64_t>(1, left);
-    }
-    rc = tb_create(&solvers[(size_t)g], pb, &o);
-    if (rc != TB_OK) { std::cerr << "tb_create failed: " << tb_last_error() << std::endl; return EXIT_FAILURE; }
+  {
+    // one host thread per GPU: context creation, uploads and attribute queries of the G devices overlap
+    std::vector<tb_status> crc((size_t)G, TB_OK);
+    std::vector<std::string> cerr_msg((size_t)G);
+    auto make = [&](int g) {
+      tb_options o;
+      memset(&o, 0, sizeof(o));
+      o.fixpoint = config.fixpoint == "ac1" ? TB_FP_AC1 : config.fixpoint == "ac1_active" ? TB_FP_AC1_ACTIVE : config.fixpoint == "wac1_active" ? TB_FP_WAC1_ACTIVE : TB_FP_WAC1;
+      o.wac1_threshold = (int32_t)config.wac1_threshold;
+      o.subproblems_power = config.subproblems_power;
+      o.subproblems_factor = (int32_t)config.subproblems_factor;
+      o.or_blocks = (int32_t)config.or_nodes;
+      o.threads_per_block = config.threads_per_block;
+      o.mem_kind = config.only_global_memory ? TB_MEM_GLOBAL : TB_MEM_AUTO;
+      o.verbose = config.verbose;
+      o.gpu_rank = g; o.gpu_world = G; o.device = g;
+      o.cutnodes = config.stop_after_n_nodes;
+      o.seed = config.seed;
+      if (config.timeout_ms) {
+        int64_t left = (int64_t)config.timeout_ms - since_ns() / 1000000;
+        o.timeout_ms = (uint64_t)std::max<int64_t>(1, left);
+      }
+      crc[(size_t)g] = tb_create(&solvers[(size_t)g], pb, &o);
+      if (crc[(size_t)g] != TB_OK) cerr_msg[(size_t)g] = tb_last_error();
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; ++g) th.emplace_back(make, g);
+    make(0);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+      if (crc[(size_t)g] != TB_OK) { std::cerr << "tb_create failed: " << cerr_msg[(size_t)g] << std::endl; return EXIT_FAILURE; }
   }
   if (G > 1) {
     rc = tb_link_peers(solvers.data(), G);
