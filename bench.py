@@ -293,6 +293,11 @@ def run_ours(args):
         if args.workload.startswith("simplified:"):
             # the same step on the network as -disable_simplify leaves it (the r01 headline before the simplifier existed)
             line["unsimplified_network"] = side_leg(engine, fpb, opts, min(args.steps, 3), flush, clocks["sm_mhz"])
+        if not args.fp.endswith("_active"):
+            # the same step with the active-set fixpoint (-fp wac1_active): same stores and search tree, but only the
+            # propagators whose variables moved are evaluated, so nodes/s is the comparable figure, not propagations/s
+            aopts = dict(opts, fixpoint=abi.FP_KINDS[args.fp + "_active"])
+            line["active_set"] = side_leg(engine, pb, aopts, min(args.steps, 3), flush, clocks["sm_mhz"])
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

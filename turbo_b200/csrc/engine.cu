@@ -230,6 +230,7 @@ struct Ctx {
   int* g_root;             // this block's snapshot (global, same layout as the store)
   int* g_snap;             // this block's snapshot ring (P.nsnap images) and its tags
   int* g_snap_tag;
+  unsigned* g_snap_flags;
   int* g_best;
   Decision* dec;
   BlockStats* st;
@@ -885,6 +886,13 @@ struct Ctx {
             const int j = c.depth - 1;
             save_store(g_snap + (size_t)(j % P.nsnap) * 2 * P.vpad);
             if (tid == 0) g_snap_tag[j % P.nsnap] = j;
+            if (ACT) {
+              // the fixpoint has just converged: no moved bit, no dirty chunk; keep the entailment cache with the image
+              const int fw = (T >> 5) * P.act_fpw / 4;
+              const unsigned* ne = act_vbits() + (P.vpad >> 5) + fw;
+              unsigned* g = g_snap_flags + (size_t)(j % P.nsnap) * fw;
+              for (int i = tid; i < fw; i += T) g[i] = ne[i];
+            }
           }
           if (tid == 0) {
             if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
@@ -907,8 +915,20 @@ struct Ctx {
           if (depth == -1) { mode = M_SOLVE_END; continue; }
           // the node where decision depth-1 was taken is in the snapshot ring unless a deeper level has reused its slot
           const bool snap = P.nsnap && *(volatile int*)(g_snap_tag + (depth - 1) % P.nsnap) == depth - 1;      // uniform (global, written before a barrier)
-          if (snap) load_store(g_snap + (size_t)((depth - 1) % P.nsnap) * 2 * P.vpad);
-          else {
+          if (snap) {
+            load_store(g_snap + (size_t)((depth - 1) % P.nsnap) * 2 * P.vpad);
+            if (ACT) {
+              // back at a converged node: every chunk is clean, its entailment cache is the one saved with the image,
+              // and only the watchers of the decision variable (marked below) are due
+              const int fw = (T >> 5) * P.act_fpw / 4, nvw = P.vpad >> 5;
+              unsigned* vb = act_vbits();
+              const unsigned* g = g_snap_flags + (size_t)((depth - 1) % P.nsnap) * fw;
+              for (int i = tid; i < nvw + fw; i += T) vb[i] = 0u;
+              for (int i = tid; i < fw; i += T) vb[nvw + fw + i] = __ldcg(g + i);
+              if (tid == 0) c.dirty_all = 0;
+              sync();
+            }
+          } else {
             load_store(g_root);
             for (int i = tid; i < depth - 1; i += T) {
               const Decision d = dec[i];
@@ -919,6 +939,7 @@ struct Ctx {
             Decision& d = dec[depth - 1];
             d.cur += 1;
             store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
+            mark_var(d.var);
             c.cur_strategy = c.snap_strategy; c.next_unassigned = c.snap_next_unassigned;
           }
           sync();
@@ -967,6 +988,7 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   k.g_best = P.block_best + (size_t)slot * 2 * P.vpad;
   k.g_snap = P.nsnap ? P.block_snap + (size_t)slot * P.nsnap * 2 * P.vpad : nullptr;
   k.g_snap_tag = P.nsnap ? P.snap_tag + (size_t)slot * P.nsnap : nullptr;
+  k.g_snap_flags = (ACT && P.nsnap) ? P.snap_flags + (size_t)slot * P.nsnap * ((blockDim.x >> 5) * P.act_fpw / 4) : nullptr;
   k.dec = P.decisions + (size_t)slot * P.max_depth;
   k.st = P.stats + slot;
   if (threadIdx.x == 0) {
@@ -1414,6 +1436,10 @@ static tb_status ensure_scratch(tb_solver* s, int slots) {
       if (dev_alloc(s, &P.block_snap, img * (size_t)slots * (size_t)n) == TB_OK && dev_alloc(s, &P.snap_tag, (size_t)slots * (size_t)n) == TB_OK) {
         if (cudaMemset(P.snap_tag, 0xff, (size_t)slots * (size_t)n * sizeof(int)) != cudaSuccess) { set_error("memset snapshot tags"); return TB_ERR_CUDA; }
         P.nsnap = n;
+        if (s->active) {
+          const size_t fw = (size_t)(s->threads / 32) * (size_t)P.act_fpw / 4;
+          if (dev_alloc(s, &P.snap_flags, std::max<size_t>(1, fw * (size_t)slots * (size_t)n)) != TB_OK) { cudaGetLastError(); P.nsnap = 0; }
+        }
       } else { cudaGetLastError(); P.block_snap = nullptr; P.snap_tag = nullptr; }    // no room: recompute on backtrack as the reference does
     }
   }

@@ -52,6 +52,7 @@ struct DevParams {
   // kept in slot j % nsnap of the block; snap_tag says which j a slot holds (-1 = none)
   int* block_snap;              // [slot][nsnap] images of 2 * vpad ints
   int* snap_tag;                // [slot][nsnap]
+  unsigned* snap_flags;         // [slot][nsnap][nwarps * act_fpw / 4]: the chunks' entailment cache at the snapshot (active set)
   int nsnap, pad2_;
   // grid-shared cells
   unsigned long long* next_subproblem;   // GridData::next_subproblem (:418), counts this GPU's shard
