@@ -182,6 +182,11 @@ typedef struct {
 } tb_layout_info;
 tb_status tb_layout_describe(const tb_problem* problem, int32_t nbanks, tb_layout_info* info, int32_t* slot_of);
 const char* tb_layout_class_name(int32_t cls);
+/* Watch lists of the active-set fixpoint: for every slot of the store image the chunks (32 propagators of the device
+ * table) that load it, as CSR (off has *nslots + 1 entries, list *nentries); chunk_of_prop[i] = chunk of propagator i.
+ * Call with NULL buffers first to get the sizes. */
+tb_status tb_layout_watch_lists(const tb_problem* problem, int32_t nbanks, int32_t* nslots, int32_t* nentries,
+                                int32_t* off, int32_t* list, int32_t* slot_of, int32_t* chunk_of_prop);
 
 void tb_destroy(tb_solver*);
 const char* tb_last_error(void);

@@ -68,3 +68,29 @@ def test_empty_and_tiny_problems():
     pb = abi.Problem([0, 0, 0], [5, 5, 5], np.array([(abi.OP_ADD, 0, 1, 2)], np.int32))
     d = engine.layout_describe(pb, 16)
     assert d["nchunks"] == 1 and d["classes"]["add_s"] == 1
+
+
+@pytest.mark.parametrize("name", ["trains15", "accap_a3", "pat1", "sudoku_opt3"])
+def test_watch_lists_cover_every_loaded_operand(name):
+    """The active-set fixpoint re-evaluates exactly the chunks on a slot's watch list when the slot moves: the chunk of
+    every propagator must be on the list of every NON-CONSTANT variable it mentions (operands that are constants at the
+    root are folded into the device word and never move), lists are sorted and duplicate free."""
+    from tests import golden_io
+    from turbo_b200 import engine
+    pb, _ = golden_io.load_simplified_problem(name)
+    off, lst, slot_of, chunk_of = engine.layout_watch_lists(pb, 16)
+    assert len(set(slot_of.tolist())) == pb.nvars and off[-1] == len(lst)
+    watch = [set(lst[off[s]:off[s + 1]].tolist()) for s in range(len(off) - 1)]
+    for s in range(len(off) - 1):
+        seg = lst[off[s]:off[s + 1]]
+        assert all(seg[i] < seg[i + 1] for i in range(len(seg) - 1))
+    p = pb.props
+    fixed = pb.lb == pb.ub
+    missing = 0
+    for i in range(pb.nprops):
+        ch = int(chunk_of[i])
+        assert ch >= 0
+        for v in (int(p["x"][i]), int(p["y"][i]), int(p["z"][i])):
+            if not fixed[v] and ch not in watch[int(slot_of[v])]:
+                missing += 1
+    assert missing == 0

@@ -223,9 +223,11 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
   // ---- watch lists: which chunks load a slot (the active-set fixpoint re-evaluates exactly those when it moves) ----
   {
     std::vector<std::vector<int>> w((size_t)L.nslots);
+    L.chunk_of_prop.assign((size_t)P, -1);
     for (size_t i = 0; i < lanes.size(); ++i) {
       if (lanes[i] < 0) continue;
       const int ch = (int)(i / 32 / TBC_U);
+      L.chunk_of_prop[(size_t)lanes[i]] = ch;
       const Item& it = items[lanes[i]];
       auto add = [&](int var) { std::vector<int>& l = w[(size_t)L.slot_of[var]]; if (l.empty() || l.back() != ch) l.push_back(ch); };
       if (loads_x(it.cls)) add(it.x);
@@ -243,6 +245,26 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
     }
     L.watch_off[(size_t)L.nslots] = (int)L.watch_list.size();
   }
+  return TB_OK;
+}
+
+extern "C" tb_status tb_layout_watch_lists(const tb_problem* pb, int32_t nbanks, int32_t* nslots, int32_t* nentries,
+                                            int32_t* off, int32_t* list, int32_t* slot_of, int32_t* chunk_of_prop) {
+  if (!pb || nbanks < 0) return TB_ERR_INVALID;
+  TnfLayoutOptions lo;
+  lo.nbanks = nbanks;
+  lo.lanes_per_set = 16;
+  lo.slot_align = nbanks > 0 ? nbanks : 4;
+  TnfLayout L;
+  std::string err;
+  tb_status rc = tb_build_layout(pb, lo, &L, &err);
+  if (rc != TB_OK) return rc;
+  if (nslots) *nslots = L.nslots;
+  if (nentries) *nentries = (int32_t)L.watch_list.size();
+  if (off) std::copy(L.watch_off.begin(), L.watch_off.end(), off);
+  if (list) std::copy(L.watch_list.begin(), L.watch_list.end(), list);
+  if (slot_of) std::copy(L.slot_of.begin(), L.slot_of.end(), slot_of);
+  if (chunk_of_prop) std::copy(L.chunk_of_prop.begin(), L.chunk_of_prop.end(), chunk_of_prop);
   return TB_OK;
 }
 

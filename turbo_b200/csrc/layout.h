@@ -26,6 +26,7 @@ struct TnfLayout {
   double wavefronts_per_load = 0.0;        // bank model: average shared-memory wavefronts per half-warp load
   bool identity = true;                    // slot_of[v] == v
   std::vector<int> watch_off, watch_list;  // slot -> chunks that load it (CSR over nslots; active-set fixpoint)
+  std::vector<int> chunk_of_prop;          // propagator -> chunk of the device table
 };
 
 struct TnfLayoutOptions {

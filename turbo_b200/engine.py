@@ -80,6 +80,22 @@ def layout_describe(problem, nbanks=16):
                 slot_of=slot_of[:problem.nvars])
 
 
+def layout_watch_lists(problem, nbanks=16):
+    """(off, list, slot_of, chunk_of_prop) of the active-set fixpoint's watch lists (host only, no GPU)."""
+    L = lib()
+    i32p = C.POINTER(C.c_int32)
+    L.tb_layout_watch_lists.argtypes = [C.POINTER(abi.TbProblem), C.c_int32, i32p, i32p, i32p, i32p, i32p, i32p]
+    L.tb_layout_watch_lists.restype = C.c_int
+    ns, ne = C.c_int32(0), C.c_int32(0)
+    _check(L.tb_layout_watch_lists(C.byref(problem.c), nbanks, C.byref(ns), C.byref(ne), None, None, None, None))
+    off = np.zeros(ns.value + 1, np.int32)
+    lst = np.zeros(max(1, ne.value), np.int32)
+    slot_of = np.zeros(max(1, problem.nvars), np.int32)
+    chunk_of = np.zeros(max(1, problem.nprops), np.int32)
+    _check(L.tb_layout_watch_lists(C.byref(problem.c), nbanks, C.byref(ns), C.byref(ne), _p(off), _p(lst), _p(slot_of), _p(chunk_of)))
+    return off, lst[:ne.value], slot_of[:problem.nvars], chunk_of[:problem.nprops]
+
+
 def device_count():
     return int(lib().tb_device_count())
 
