@@ -159,3 +159,40 @@ def test_other_placements_fall_back_to_the_dense_sweeps(eng, orc):
         with eng.Solver(pb, mem_kind=kind, fixpoint=abi.FP_WAC1_ACTIVE) as s:
             g = s.propagate()
         assert_same_store(g, o, kind)
+
+
+# ---- snapshot ring for backtracking (copying instead of recomputation) --------------------------------------------------
+
+@pytest.mark.parametrize("levels", ["0", "2", "3", "64"])
+@pytest.mark.parametrize("fp", [abi.FP_WAC1, abi.FP_AC1_ACTIVE, abi.FP_WAC1_ACTIVE])
+def test_snapshot_ring_sizes_keep_the_search_trace(eng, orc, monkeypatch, levels, fp):
+    """0 = the reference's restore-from-root + replay; 2 and 3 levels force slot reuse and the fallback on almost every
+    backtrack; 64 is the default. The oracle always recomputes: same nodes, failures, solutions, depth, optimum."""
+    monkeypatch.setenv("TB_SNAPSHOT_LEVELS", levels)
+    for seed in range(10):
+        pb = tnf_gen.search_instance(seed) if seed < 7 else tnf_gen.random_net(18, 10, 4000 + seed, lo=-4, hi=4)
+        for depth in (0, 3):
+            o = orc.solve(pb, depth=depth)
+            for kind in SHARED + [abi.MEM_GLOBAL]:
+                with eng.Solver(pb, or_blocks=1, subproblems_power=depth, fixpoint=fp, mem_kind=kind) as s:
+                    g = s.solve()
+                for key in ("nodes", "fails", "solutions", "eps_solved_subproblems", "eps_skipped_subproblems", "depth_max"):
+                    assert g["stats"][key] == o["stats"][key], (levels, seed, depth, kind, key, g["stats"][key], o["stats"][key])
+                assert g["objective"] == o["objective"]
+
+
+@pytest.mark.parametrize("levels", ["0", "2", "64"])
+def test_snapshot_ring_on_a_deep_search(eng, monkeypatch, levels):
+    """trains15 dives hundreds of levels deep: one block, 600 nodes, dense and active-set walk the same tree whatever the ring."""
+    monkeypatch.setenv("TB_SNAPSHOT_LEVELS", levels)
+    pb, info = golden_io.load_simplified_problem("trains15")
+    res = []
+    for fp in (abi.FP_WAC1, abi.FP_WAC1_ACTIVE):
+        with eng.Solver(pb, or_blocks=1, subproblems_power=4, cutnodes=600, fixpoint=fp) as s:
+            r = s.solve()
+        res.append((r["stats"]["nodes"], r["stats"]["fails"], r["stats"]["solutions"], r["stats"]["depth_max"], r["objective"]))
+    assert res[0] == res[1]
+    assert res[0] == test_snapshot_ring_on_a_deep_search.expected.setdefault("trace", res[0])
+
+
+test_snapshot_ring_on_a_deep_search.expected = {}

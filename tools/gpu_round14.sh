@@ -1,0 +1,32 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out
+( time timeout 1200 python -m pytest tests/test_gpu_active.py -m gpu -x -q -k "snapshot" ) > $O/pytest_ring.log 2>&1
+tail -5 $O/pytest_ring.log
+B="python bench.py --no-cpu-baseline --no-fixpoint-leg"
+run() { echo "== $*" >> $O/exp14.log; timeout 300 "$@" >> $O/exp14.log 2>> $O/exp14.err; }
+for w in simplified:trains15 trains15 simplified:example_wordpress7_500; do
+  run $B --workload $w
+  run env TURBO_B200_LIB=$PWD/turbo_b200/variants/libturbo_b200_pf1.so $B --workload $w
+  run env TURBO_B200_LIB=$PWD/turbo_b200/variants/libturbo_b200_pf2.so $B --workload $w
+done
+for v in "" pf1 pf2; do
+  echo "== fixpoint kernel trains15 variant=$v" >> $O/exp14.log
+  if [ -z "$v" ]; then timeout 120 python tools/fixpoint_bench.py --workload trains15 >> $O/exp14.log 2>> $O/exp14.err
+  else TURBO_B200_LIB=$PWD/turbo_b200/variants/libturbo_b200_$v.so timeout 120 python tools/fixpoint_bench.py --workload trains15 >> $O/exp14.log 2>> $O/exp14.err; fi
+done
+python - <<'PY'
+import json
+for line in open("gpurun_out/exp14.log"):
+    line = line.strip()
+    if line.startswith("{"):
+        d = json.loads(line)
+        if "config" in d:
+            c = d["config"]
+            print("   %s tpb %d blocks %d | Gprop/s %.1f nodes/s %.0f frac %.4f" % (c["memory_configuration"], c["threads_per_block"], c["num_blocks_per_gpu"], d["value"] / 1e9, d["nodes_per_sec"], d["roofline"]["frac"]))
+        else:
+            print("   fixpoint kernel Gprop/s %.1f frac %.4f ms %.3f" % (d["propagations_per_sec"] / 1e9, d["smem_frac"], d["kernel_ms"]))
+    else:
+        print(line)
+PY
+tail -3 $O/exp14.err

@@ -323,7 +323,7 @@ struct Ctx {
   };
 
   // A chunk's words are requested at the end of the visit before the previous one. The global table is followed
-  // by 64 chunks of padding, so the prefetch needs no bound check; the shared copy (TCN_SHARED) is not, and clamps.
+  // by 160 chunks of padding, so the prefetch needs no bound check; the shared copy (TCN_SHARED) is not, and clamps.
   __device__ __forceinline__ Words load_words(const unsigned long long* words, int i) const {
     Words r;
     if (MEM == TB_MEM_TCN_SHARED) i = min(i, (P.nchunks * 32 - 1) * TBC_U);
@@ -1426,10 +1426,10 @@ static tb_status ensure_scratch(tb_solver* s, int slots) {
   if ((rc = dev_alloc(s, &P.decisions, (size_t)P.max_depth * slots))) return rc;
   {
     // snapshot ring: as many levels as a memory budget allows (TB_SNAPSHOT_MB, default 4096 MB per GPU; 0 disables),
-    // at most 64 per block
+    // at most 64 per block (TB_SNAPSHOT_LEVELS lowers that: the tests run rings of 2 and 3 levels to exercise slot reuse)
     const size_t budget = (size_t)std::max(0, env_int("TB_SNAPSHOT_MB", 4096)) << 20;
     const size_t per_level = img * sizeof(int) * (size_t)slots;
-    int n = (int)std::min<size_t>(64, per_level ? budget / per_level : 0);
+    int n = (int)std::min<size_t>((size_t)std::max(0, std::min(64, env_int("TB_SNAPSHOT_LEVELS", 64))), per_level ? budget / per_level : 0);
     if (s->opt.max_depth > 0) n = std::min(n, s->opt.max_depth);
     P.nsnap = 0; P.block_snap = nullptr; P.snap_tag = nullptr;
     if (n >= 2) {
@@ -1545,9 +1545,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   {
     const TnfLayout& L = s->layout;
     unsigned long long* d = nullptr;
-    // 64 chunks of padding behind the table: a warp prefetches two visits ahead without a bound check
-    if ((rc = dev_alloc(s, &d, L.words.size() + 64 * 32 * TBC_U))) return fail(rc);
-    if (cudaMemset(d, 0, (L.words.size() + 64 * 32 * TBC_U) * 8) != cudaSuccess ||
+    // 160 chunks of padding behind the table: a warp prefetches up to five visits ahead without a bound check
+    if ((rc = dev_alloc(s, &d, L.words.size() + 160 * 32 * TBC_U))) return fail(rc);
+    if (cudaMemset(d, 0, (L.words.size() + 160 * 32 * TBC_U) * 8) != cudaSuccess ||
         (L.words.size() && cudaMemcpy(d, L.words.data(), L.words.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
     P.words = d;
     if (s->active) {
