@@ -90,3 +90,18 @@ def test_product_never_links_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f)).read()
                 assert "tnf_oracle" not in text and "oracle_py" not in text, os.path.join(dirpath, f)
+
+
+def test_minizinc_solver_entry():
+    """The .msc MiniZinc reads (reference benchmarks/minizinc/turbo.gpu.release.msc): valid JSON, points at the built
+    driver and at a solver library that compiles set variables away, advertises the flags the driver parses."""
+    import json
+    d = os.path.join(ROOT, "turbo_b200", "minizinc")
+    msc = json.load(open(os.path.join(d, "turbo.b200.release.msc")))
+    assert os.path.exists(os.path.normpath(os.path.join(d, msc["executable"])))
+    assert "nosets.mzn" in open(os.path.join(d, msc["mznlib"], "redefinitions.mzn")).read()
+    assert msc["supportsFzn"] and not msc["supportsMzn"] and set(["-a", "-n", "-p", "-s", "-v", "-f", "-t"]) <= set(msc["stdFlags"])
+    exe = os.path.join(ROOT, "turbo_b200", "bin", "turbo")
+    usage = subprocess.run([exe], capture_output=True, text=True).stdout
+    for flag, *_ in msc["extraFlags"]:
+        assert flag in usage or flag in ("-timeout",), flag
