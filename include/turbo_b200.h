@@ -68,7 +68,8 @@ typedef struct {
  * The ..._ACTIVE kinds (the reference's FixpointSubsetGPU idea, barebones :636,984) keep the same
  * sweeps but a warp only evaluates the chunks of 32 propagators one of whose variables changed since the chunk was
  * last evaluated; same fixpoints, same search, fewer evaluations (num_deductions counts what was evaluated). They
- * apply to the shared-memory placements; elsewhere they behave like the plain kinds. */
+ * apply to the shared-memory placements and to tables of at least 128 chunks (TB_ACTIVE_MIN_CHUNKS); elsewhere they
+ * behave like the plain kinds. */
 typedef enum { TB_FP_AC1 = 0, TB_FP_WAC1 = 1, TB_FP_AC1_ACTIVE = 2, TB_FP_WAC1_ACTIVE = 3 } tb_fixpoint_kind;
 
 /* Store placement (MemoryKind, include/memory_gpu.hpp:18-22) plus the B200 cluster/DSMEM tier. */

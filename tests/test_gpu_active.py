@@ -15,6 +15,12 @@ ACTIVE = [abi.FP_AC1_ACTIVE, abi.FP_WAC1_ACTIVE]
 SHARED = [abi.MEM_TCN_SHARED, abi.MEM_STORE_SHARED]
 
 
+@pytest.fixture(autouse=True)
+def force_active_on_small_networks(monkeypatch):
+    # the engine runs the plain sweeps below 128 chunks (they are faster there); these tests want the active path
+    monkeypatch.setenv("TB_ACTIVE_MIN_CHUNKS", "0")
+
+
 @pytest.fixture(scope="module")
 def eng():
     from turbo_b200 import engine
@@ -196,3 +202,15 @@ def test_snapshot_ring_on_a_deep_search(eng, monkeypatch, levels):
 
 
 test_snapshot_ring_on_a_deep_search.expected = {}
+
+
+def test_small_networks_run_the_plain_sweeps_by_default(eng, orc, monkeypatch):
+    monkeypatch.delenv("TB_ACTIVE_MIN_CHUNKS", raising=False)
+    pb = tnf_gen.planted(500, 1500, 3)              # 47+ chunks: under the threshold
+    o = orc.fixpoint(pb)
+    with eng.Solver(pb, fixpoint=abi.FP_WAC1_ACTIVE) as s:
+        g = s.propagate()
+    with eng.Solver(pb, fixpoint=abi.FP_WAC1) as s:
+        d = s.propagate()
+    assert_same_store(g, o, "default threshold")
+    assert g["stats"]["num_deductions"] == d["stats"]["num_deductions"]

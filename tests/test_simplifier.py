@@ -159,3 +159,23 @@ def test_gpu_solves_the_reduced_network_to_the_reference_optimum(name):
     assert m.check_tnf(r["lb"]) == 0
     flb, fub = m.expand(r["lb"], r["ub"])
     assert golden_io.user_objective(info, flb, fub) == info["expected"]
+
+
+def test_satisfaction_problems_and_strategies_after_simplification():
+    from oracle import oracle_py as orc
+    m = Model.from_fzn_text(
+        "var 1..4: a :: output_var;\nvar 1..4: b :: output_var;\nvar 1..4: c :: output_var;\nvar 1..4: d :: output_var;\nvar bool: p;\n"
+        "constraint int_ne(a, b);\nconstraint int_ne(b, c);\nconstraint int_ne(a, c);\nconstraint int_eq(c, d);\n"
+        "constraint int_lin_le([1,1],[a,b],4);\nconstraint int_le_reif(a, b, p);\nconstraint bool_eq(p, true);\n"
+        "solve :: int_search([d, c, b, a], input_order, indomain_max, complete) satisfy;\n")
+    full_strategies = [list(vs) for _, _, vs in m.problem.strategies]
+    st = m.simplify(oracle_fixpoint)
+    assert st["merged_variables"] >= 1                       # c == d
+    # the user's strategy survives on representatives, without duplicates, in the same order; the default stays last
+    (vo, va, vs), (dvo, dva, dvs) = m.problem.strategies[0], m.problem.strategies[-1]
+    assert va == abi.VAL_MAX and len(vs) == len(set(vs.tolist())) and 1 <= len(vs) <= len(full_strategies[0]) and len(dvs) == 0
+    r = orc.solve(m.problem, depth=0)
+    assert r["has_solution"] and m.check_solution(r["lb"]) == 0
+    vals = dict(line.rstrip(";").split(" = ") for line in m.format_solution(r["lb"]).strip().splitlines())
+    a, b, c, d = (int(vals[k]) for k in "abcd")
+    assert len({a, b, c}) == 3 and c == d and a + b <= 4 and a <= b

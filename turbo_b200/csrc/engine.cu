@@ -1358,7 +1358,10 @@ static tb_status configure(tb_solver* s) {
 // Active-set fixpoint: exact size and position of its flags once the layout pass has fixed the store image and the
 // placement policy the thread count.  Shared-memory placements only; elsewhere the plain sweeps run.
 static void place_active(tb_solver* s) {
-  s->active = s->want_active && (s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED);
+  // Small tables are cheaper to sweep densely than to track (accap_a3, 32 chunks: 25 M nodes/s dense, 13.5 M active;
+  // trains15, 420 chunks: 5.7 M dense, 8.4 M active): below TB_ACTIVE_MIN_CHUNKS (default 128) the plain kind runs.
+  s->active = s->want_active && (s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED) &&
+              s->P.nchunks >= env_int("TB_ACTIVE_MIN_CHUNKS", 128);
   s->P.act_off = 0; s->P.act_fpw = 0;
   if (!s->active) return;
   const int nwarps = s->threads / 32;

@@ -423,6 +423,7 @@ int main(int argc, char** argv) {
   std::vector<tb_status> rcs((size_t)G, TB_OK);
   if (config.verbose) printf("%% GPU kernel started, starting solving...\n");
   const int64_t kernel_start_ns = since_ns();
+  if (config.verbose) printf("%% start-up: preprocessing (parse, ternarise, simplify on the GPU) %.3f s, engine creation %.3f s\n", to_sec(init_ns), to_sec(kernel_start_ns - init_ns));
   {
     std::vector<std::thread> th;
     for (int g = 0; g < G; ++g)
