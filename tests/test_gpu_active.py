@@ -205,12 +205,19 @@ test_snapshot_ring_on_a_deep_search.expected = {}
 
 
 def test_small_networks_run_the_plain_sweeps_by_default(eng, orc, monkeypatch):
-    monkeypatch.delenv("TB_ACTIVE_MIN_CHUNKS", raising=False)
-    pb = tnf_gen.planted(500, 1500, 3)              # 47+ chunks: under the threshold
+    """Under 128 chunks the *_ACTIVE kinds run the plain sweeps: no flag area is reserved next to the store."""
+    pb = tnf_gen.planted(500, 1500, 3)              # about 50 chunks
     o = orc.fixpoint(pb)
-    with eng.Solver(pb, fixpoint=abi.FP_WAC1_ACTIVE) as s:
-        g = s.propagate()
-    with eng.Solver(pb, fixpoint=abi.FP_WAC1) as s:
-        d = s.propagate()
-    assert_same_store(g, o, "default threshold")
-    assert g["stats"]["num_deductions"] == d["stats"]["num_deductions"]
+    shared = {}
+    for min_chunks in ("0", None):
+        if min_chunks is None:
+            monkeypatch.delenv("TB_ACTIVE_MIN_CHUNKS", raising=False)
+        else:
+            monkeypatch.setenv("TB_ACTIVE_MIN_CHUNKS", min_chunks)
+        for fp in (abi.FP_WAC1, abi.FP_WAC1_ACTIVE):
+            with eng.Solver(pb, fixpoint=fp, mem_kind=abi.MEM_TCN_SHARED) as s:
+                shared[(min_chunks, fp)] = s.config()["shared_bytes"]
+                g = s.propagate()
+            assert_same_store(g, o, (min_chunks, fp))
+    assert shared[("0", abi.FP_WAC1_ACTIVE)] > shared[("0", abi.FP_WAC1)]
+    assert shared[(None, abi.FP_WAC1_ACTIVE)] == shared[(None, abi.FP_WAC1)] == shared[("0", abi.FP_WAC1)]
