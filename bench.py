@@ -225,6 +225,7 @@ def run_ours(args):
     # ---- e2e: host buffers -> tb_create (H2D) -> tb_solve -> results (D2H) -> tb_destroy -------------------
     e2e_ded, e2e_s = 0, 0.0
     e2e_steps = max(1, min(args.steps, 3))
+    solver.close()                           # its device memory goes back to the pool the e2e solvers allocate from
     barrier()
     for _ in range(e2e_steps):
         t = time.perf_counter()
@@ -278,7 +279,6 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(pb, cfg["subproblems_power"], args)
-    solver.close()
     if rank == 0 and world == 1 and not args.no_fixpoint_leg:
         # the fixpoint kernel alone (the kernel SURVEY.md 8(d)'s shared-memory roofline is stated for): root fixpoints of
         # the FULL network (a simplified network is already at its root fixpoint: one sweep and nothing to narrow)
