@@ -538,11 +538,21 @@ struct Ctx {
             nz &= nz - 1;
             const unsigned mw = __shfl_sync(0xffffffffu, m, src);
             if ((mw >> lane) & 1u) {
+              // one 64-bit word names the slot's first three watchers (one L2 round trip); the few slots with more
+              // continue through the CSR list
               const int v = ((base + src) << 5) + lane;
-              const int e = __ldg(P.watch_off + v + 1);
-              for (int k = __ldg(P.watch_off + v); k < e; ++k) {
-                const int ch = __ldg(P.watch_list + k);
-                dirty[(ch & (nwarps - 1)) * FPW + (ch >> lw)] = 1;
+              const unsigned long long wd = __ldg(P.watch_inline + v);
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const unsigned id = (unsigned)(wd >> (16 * k)) & 0xFFFFu;
+                if (id != 0xFFFFu) dirty[(id & (unsigned)(nwarps - 1)) * FPW + (id >> lw)] = 1;
+              }
+              if ((unsigned)(wd >> 48) == 0xFFFEu) {
+                const int e = __ldg(P.watch_off + v + 1);
+                for (int k = __ldg(P.watch_off + v) + 3; k < e; ++k) {
+                  const int ch = __ldg(P.watch_list + k);
+                  dirty[(ch & (nwarps - 1)) * FPW + (ch >> lw)] = 1;
+                }
               }
             }
           }
@@ -1358,10 +1368,7 @@ static tb_status configure(tb_solver* s) {
 // Active-set fixpoint: exact size and position of its flags once the layout pass has fixed the store image and the
 // placement policy the thread count.  Shared-memory placements only; elsewhere the plain sweeps run.
 static void place_active(tb_solver* s) {
-  // Small tables are cheaper to sweep densely than to track (accap_a3, 32 chunks: 25 M nodes/s dense, 13.5 M active;
-  // trains15, 420 chunks: 5.7 M dense, 8.4 M active): below TB_ACTIVE_MIN_CHUNKS (default 128) the plain kind runs.
-  s->active = s->want_active && (s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED) &&
-              s->P.nchunks >= env_int("TB_ACTIVE_MIN_CHUNKS", 128);
+  s->active = s->want_active && (s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED);
   s->P.act_off = 0; s->P.act_fpw = 0;
   if (!s->active) return;
   const int nwarps = s->threads / 32;
@@ -1515,6 +1522,10 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     s->prop_bytes = (size_t)nchunks * 32 * TBC_U * 8;
     s->store_bytes = (size_t)std::max(32, (pb->nvars + 31) / 32 * 32) * 8;     // shared placements pad to the 32 banks
   }
+  // Small tables are cheaper to sweep densely than to track (accap_a3, 32 chunks: 25 M nodes/s dense, 13.5 M active;
+  // trains15, 420 chunks: 5.7 M dense, 8.4 M active): below TB_ACTIVE_MIN_CHUNKS (default 128) the plain kind runs
+  // and no flag area is reserved. Chunk ids must fit the 16-bit fields of the watch words.
+  if (P.nchunks < env_int("TB_ACTIVE_MIN_CHUNKS", 128) || P.nchunks >= 0xFFFE) s->want_active = false;
   if ((rc = configure(s)) != TB_OK) return fail(rc);
   {
     TnfLayoutOptions lo;
@@ -1560,6 +1571,10 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
       if (cudaMemcpy(wo, L.watch_off.data(), L.watch_off.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
           (L.watch_list.size() && cudaMemcpy(wl, L.watch_list.data(), L.watch_list.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D watch lists"); return fail(TB_ERR_CUDA); }
       P.watch_off = wo; P.watch_list = wl;
+      unsigned long long* wi = nullptr;
+      if ((rc = dev_alloc(s, &wi, std::max<size_t>(1, L.watch_inline.size())))) return fail(rc);
+      if (L.watch_inline.size() && cudaMemcpy(wi, L.watch_inline.data(), L.watch_inline.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D watch words"); return fail(TB_ERR_CUDA); }
+      P.watch_inline = wi;
     }
     std::vector<int> var_of((size_t)P.vpad, -1);
     for (int v = 0; v < pb->nvars; ++v) var_of[L.slot_of[v]] = v;

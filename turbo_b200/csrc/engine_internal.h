@@ -62,6 +62,7 @@ struct DevParams {
   // active-set fixpoint (TB_FP_*_ACTIVE): slot -> chunks that load it (CSR), and where its flags live in shared memory
   const int* watch_off;                  // vpad + 1 offsets into watch_list
   const int* watch_list;                 // chunk ids, ascending per slot
+  const unsigned long long* watch_inline; // per slot: its first three watchers as 16-bit chunk ids (0xFFFF = none), top 16 bits 0xFFFE = more in the CSR list
   int act_off;                           // byte offset of the active-set area in dynamic shared memory
   int act_fpw;                           // chunk flags per warp (multiple of 32): chunk ch is flag (ch / nwarps) of warp (ch % nwarps)
 };

@@ -244,6 +244,15 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
       L.watch_list.insert(L.watch_list.end(), l.begin(), l.end());
     }
     L.watch_off[(size_t)L.nslots] = (int)L.watch_list.size();
+    // one 64-bit word per slot answers most marks with a single load: three watchers inline, a flag for "more"
+    L.watch_inline.assign((size_t)L.nslots, ~0ull);
+    for (int sl = 0; sl < L.nslots; ++sl) {
+      const int b = L.watch_off[(size_t)sl], e = L.watch_off[(size_t)sl + 1];
+      uint64_t wd = 0;
+      for (int k = 0; k < 3; ++k) wd |= (uint64_t)(b + k < e ? (uint32_t)L.watch_list[(size_t)(b + k)] & 0xFFFFu : 0xFFFFu) << (16 * k);
+      wd |= (uint64_t)(e - b > 3 ? 0xFFFEu : 0xFFFFu) << 48;
+      L.watch_inline[(size_t)sl] = wd;
+    }
   }
   return TB_OK;
 }

@@ -27,6 +27,7 @@ struct TnfLayout {
   bool identity = true;                    // slot_of[v] == v
   std::vector<int> watch_off, watch_list;  // slot -> chunks that load it (CSR over nslots; active-set fixpoint)
   std::vector<int> chunk_of_prop;          // propagator -> chunk of the device table
+  std::vector<uint64_t> watch_inline;      // per slot: first three watchers as 16-bit ids (0xFFFF = none), top 16 bits 0xFFFE = more in the list
 };
 
 struct TnfLayoutOptions {
