@@ -6,8 +6,8 @@
 //   * one persistent CTA per search worker; the interval store lives in shared memory
 //     (STORE_SHARED / TCN_SHARED), striped over a thread-block cluster's distributed shared memory
 //     (STORE_CLUSTER, cluster.cu) or in L2-resident global memory (GLOBAL);
-//   * propagators are immutable, packed to 8 bytes (op:4 | x:20 | y:20 | z:20) when #vars <= 2^20
-//     and streamed coalesced (one 64-bit load per lane) from L2, or staged once into shared memory;
+//   * propagators are immutable, sorted into classes (tnf_classes.h) and packed to one 64-bit word of three
+//     21-bit fields, streamed coalesced (one 64-bit load per lane) from L2, or staged once into shared memory;
 //   * the fixpoint loop publishes narrowed bounds with shared-memory atomicMax/atomicMin, detects
 //     "changed / failed / not entailed" with a warp REDUX + one atomicOr per warp into a rotating
 //     three-slot flag word: one __syncthreads per sweep; entailment (`ask`) is fused into the
@@ -15,7 +15,10 @@
 //   * snapshot / restore-from-root / best-store copies are TMA bulk copies (cp.async.bulk) between
 //     global and shared memory, completion tracked by an mbarrier;
 //   * branching, the decision stack with ropes, the EPS dive and the subproblem dispenser all run
-//     in the kernel: no host round trip per node.
+//     in the kernel: no host round trip per node;
+//   * backtracking reloads the fixpoint of the node where the decision was taken from a ring of store images in
+//     HBM (copying instead of the reference's recomputation from the subproblem root; same stores, same tree);
+//   * the *_ACTIVE fixpoint kinds only evaluate the chunks whose variables moved (same fixpoints, fewer evaluations).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
