@@ -529,21 +529,16 @@ struct Ctx {
         for (int i = tid; i < nwarps * FPW; i += T) { const int w = i / FPW, k = i - w * FPW; dirty[i] = (k * nwarps + w) < P.nchunks ? 1 : 0; }
         for (int i = tid; i < nvw; i += T) vbits[i] = 0;
       } else {
-        // warp-cooperative: a warp takes 32 words at a time; for every non-zero word, lane l follows the watch list of
-        // slot 32 * word + l, so the L2 round trips of up to 32 moved slots overlap instead of queueing in one thread
-        for (int base = warp * 32; base < nvw; base += nwarps * 32) {
-          const int i = base + lane;
-          unsigned m = i < nvw ? vbits[i] : 0u;
-          if (m) vbits[i] = 0;
-          unsigned nz = __ballot_sync(0xffffffffu, m != 0u);
-          while (nz) {
-            const int src = __ffs((int)nz) - 1;
-            nz &= nz - 1;
-            const unsigned mw = __shfl_sync(0xffffffffu, m, src);
-            if ((mw >> lane) & 1u) {
-              // one 64-bit word names the slot's first three watchers (one L2 round trip); the few slots with more
-              // continue through the CSR list
-              const int v = ((base + src) << 5) + lane;
+        // every thread follows the watchers of the moved slots of its own words (moved slots are spread thinly over the
+        // words, so the lanes of a warp work on different slots at the same time: one L2 round trip per round of bits);
+        // one 64-bit word names a slot's first three watchers, the few slots with more continue through the CSR list
+        for (int i = tid; i < nvw; i += T) {
+          unsigned m = vbits[i];
+          if (m) {
+            vbits[i] = 0;
+            do {
+              const int v = (i << 5) + __ffs((int)m) - 1;
+              m &= m - 1;
               const unsigned long long wd = __ldg(P.watch_inline + v);
 #pragma unroll
               for (int k = 0; k < 3; ++k) {
@@ -557,7 +552,7 @@ struct Ctx {
                   dirty[(ch & (nwarps - 1)) * FPW + (ch >> lw)] = 1;
                 }
               }
-            }
+            } while (m);
           }
         }
       }
