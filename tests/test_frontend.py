@@ -219,3 +219,83 @@ def test_synthetic_generator_is_deterministic_and_satisfiable(tmp_path):
     c = Model.from_tnf(p)
     assert np.array_equal(a.problem.ub, c.problem.ub) and np.array_equal(a.problem.props, c.problem.props)
     assert len(c.problem.strategies) == len(a.problem.strategies)
+
+
+# ---- set variables (membership Booleans; unsolved_bugs_data/valve6.fzn was flattened without nosets.mzn) -------------
+
+def gen_set_model(rng):
+    """x, y in 0..5, idx in 1..3, b Boolean, S = arr[idx] (array_set_element), b <-> y in S (set_in_reif), optionally x in S."""
+    universe = (1, 4)
+    arr = []
+    for _ in range(3):
+        vals = sorted(set(int(v) for v in rng.integers(universe[0], universe[1] + 1, size=int(rng.integers(0, 4)))))
+        arr.append(vals)
+    hard = bool(rng.random() < 0.5)
+    coef = [int(v) for v in rng.integers(-3, 4, size=4)]
+    bound = int(rng.integers(-4, 8))
+    sense = "minimize" if rng.random() < 0.5 else "maximize"
+    lit = lambda vs: "{" + ",".join(map(str, vs)) + "}"
+    text = "\n".join([
+        f"array [1..3] of set of int: sets = [{','.join(lit(v) for v in arr)}];",
+        "var 0..5: x :: output_var;", "var 0..5: y :: output_var;", "var 1..3: idx :: output_var;", "var bool: b :: output_var;",
+        "var 0..1: bi :: output_var;", "var -40..40: obj :: output_var;",
+        f"var set of {universe[0]}..{universe[1]}: S;",
+        "constraint array_set_element(idx, sets, S);",
+        "constraint set_in_reif(y, S, b);",
+        "constraint bool2int(b, bi);",
+    ] + (["constraint set_in(x, S);"] if hard else []) + [
+        f"constraint int_lin_le([{coef[0]},{coef[1]},{coef[2]}],[x,y,idx],{bound});",
+        f"constraint int_lin_eq([{coef[0]},{coef[3]},2,3,-1],[x,y,idx,bi,obj],0);",
+        f"solve {sense} obj;"])
+    best = None
+    for x in range(6):
+        for y in range(6):
+            for idx in range(1, 4):
+                S = set(arr[idx - 1])
+                b = int(y in S)
+                if hard and x not in S:
+                    continue
+                if coef[0] * x + coef[1] * y + coef[2] * idx > bound:
+                    continue
+                obj = coef[0] * x + coef[3] * y + 2 * idx + 3 * b
+                if best is None or (obj < best if sense == "minimize" else obj > best):
+                    best = obj
+    return text, best
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_set_variable_models_match_bruteforce(seed):
+    rng = np.random.default_rng(1000 + seed)
+    text, best = gen_set_model(rng)
+    m = Model.from_fzn_text(text)
+    if m.root_failed:
+        assert best is None, text
+        return
+    r = orc.solve(m.problem, depth=2)
+    assert r["exhaustive"]
+    assert r["has_solution"] == (best is not None), text
+    if best is not None:
+        assert m.user_objective(r["lb"], r["ub"]) == best, text
+        assert m.check_solution(r["lb"]) == 0, text
+
+
+def test_set_variable_checker_and_errors():
+    text = ("array [1..2] of set of int: sets = [{1,2},{3}];\nvar 1..2: i :: output_var;\nvar 0..4: x :: output_var;\nvar bool: b :: output_var;\n"
+            "var set of 1..3: S;\nconstraint array_set_element(i, sets, S);\nconstraint set_in_reif(x, S, b);\nsolve satisfy;\n")
+    m = Model.from_fzn_text(text)
+    r = orc.solve(m.problem, depth=0)
+    assert r["has_solution"] and m.check_solution(r["lb"]) == 0
+    # flip the reified result: the checker must object (the set constraint is evaluated on the membership variables)
+    bad = r["lb"].copy()
+    vals = dict(line.rstrip(";").split(" = ") for line in m.format_solution(r["lb"]).strip().splitlines())
+    assert (vals["b"] == "true") == (int(vals["x"]) in ({1, 2} if vals["i"] == "1" else {3}))
+    with pytest.raises(Exception):
+        Model.from_fzn_text("var set of 1..3: S :: output_var;\nsolve satisfy;\n")
+    with pytest.raises(Exception):
+        Model.from_fzn_text("var set of int: S;\nsolve satisfy;\n")
+
+
+def test_unsolved_bugs_valve6_goes_through_the_front_end(reference_dir):
+    import os
+    m = Model.from_fzn(os.path.join(reference_dir, "benchmarks", "unsolved_bugs_data", "valve6.fzn"))
+    assert m.problem.nvars > 10000 and m.objective_kind == 1 and not m.root_failed

@@ -242,7 +242,7 @@ struct Parser {
 
   int declare_var(const std::string& name, const TypeSpec& t, const std::vector<Expr>& anns) {
     if (t.is_float) lx.fail("float variables are not supported ('" + name + "')");
-    if (t.is_set) lx.fail("set variables are not supported ('" + name + "')");
+    if (t.is_set) lx.fail("arrays of set variables are not supported ('" + name + "')");
     Var v;
     v.name = name;
     v.is_bool = t.is_bool;
@@ -265,11 +265,40 @@ struct Parser {
     return idx;
   }
 
+  // `var set of <universe>: name`: one Boolean membership variable per universe value, bound to `name` as a SETVAR
+  void declare_set_var(const std::string& name, const TypeSpec& t, const std::vector<Expr>& anns) {
+    if (!t.has_bounds) lx.fail("set variable '" + name + "' needs a finite universe");
+    if (find_ann(anns, "output_var")) lx.fail("output of set variables is not supported ('" + name + "')");
+    std::vector<int64_t> universe = t.values;
+    if (universe.empty()) for (int64_t v = t.lb; v <= t.ub; ++v) universe.push_back(v);
+    if (universe.size() > 4096) lx.fail("the universe of set variable '" + name + "' is too large");
+    Expr s;
+    normalize_set(universe, s);
+    s.kind = Expr::SETVAR;
+    TypeSpec b;
+    b.is_bool = true; b.has_bounds = true; b.lb = 0; b.ub = 1;
+    std::vector<Expr> intro;
+    Expr tag; tag.kind = Expr::IDENT; tag.name = "var_is_introduced";
+    intro.push_back(tag);
+    for (int64_t v : universe) {
+      Expr e; e.kind = Expr::VAR;
+      e.var = declare_var(name + "{" + std::to_string(v) + "}", b, intro);
+      s.elems.push_back(e);
+    }
+    m->names[name] = s;
+  }
+
   void parse_var_decl() {            // after 'var'
     TypeSpec t = parse_type();
     lx.expect_sym(":");
     std::string name = lx.expect_ident();
     std::vector<Expr> anns = parse_annotations();
+    if (t.is_set) {
+      declare_set_var(name, t, anns);
+      if (lx.is_sym("=")) lx.fail("initialised set variables are not supported ('" + name + "')");
+      lx.expect_sym(";");
+      return;
+    }
     int idx = declare_var(name, t, anns);
     if (lx.accept_sym("=")) {
       Expr e = parse_expr();

@@ -4,7 +4,9 @@
 // the parser itself is an un-vendored dependency).  Covers the FlatZinc subset of SURVEY.md
 // Appendix B: parameter arrays, bounded / boolean / set-literal variable declarations, variable
 // arrays mixing identifiers and literals, output annotations, nested predicate calls used as terms
-// (test_data/bug1.fzn), solve items with int_search / bool_search / seq_search.
+// (test_data/bug1.fzn), solve items with int_search / bool_search / seq_search. A set variable `var set of lo..hi`
+// is declared as one Boolean membership variable per value of its universe (what MiniZinc's nosets.mzn does at the
+// model level; unsolved_bugs_data/valve6.fzn was flattened without it).
 #pragma once
 #include <cstdint>
 #include <map>
@@ -22,11 +24,11 @@ struct ParseError {
 
 // A term after identifier resolution.
 struct Expr {
-  enum Kind { INT, BOOL, VAR, ARRAY, SET, CALL, STRING, IDENT } kind = INT;
+  enum Kind { INT, BOOL, VAR, ARRAY, SET, CALL, STRING, IDENT, SETVAR } kind = INT;
   int64_t value = 0;                    // INT / BOOL literal
   int var = -1;                         // VAR: index into Model::vars
-  std::vector<Expr> elems;              // ARRAY elements / CALL arguments
-  std::vector<std::pair<int64_t, int64_t>> ranges;  // SET: sorted disjoint ranges
+  std::vector<Expr> elems;              // ARRAY elements / CALL arguments / SETVAR: one membership variable per universe value (ascending)
+  std::vector<std::pair<int64_t, int64_t>> ranges;  // SET: sorted disjoint ranges; SETVAR: its universe
   std::string name;                     // CALL / IDENT / STRING text
 };
 

@@ -273,6 +273,62 @@ struct Builder {
     chain(TB_OP_MAX, members, r);
   }
 
+  // ---- set variables: one membership Boolean per universe value (fzn_parser.cpp, declare_set_var) -----------------
+  static std::vector<int64_t> universe_of(const Expr& s) {
+    std::vector<int64_t> u;
+    for (const auto& rg : s.ranges) for (int64_t v = rg.first; v <= rg.second; ++v) u.push_back(v);
+    return u;
+  }
+  static bool set_has(const Expr& s, int64_t v) {
+    for (const auto& rg : s.ranges) if (v >= rg.first && v <= rg.second) return true;
+    return false;
+  }
+
+  // r = (x in S), S a set variable: (x = v) => (r = member_v) for every universe value, and r => x in universe
+  void set_in_var(int x, const Expr& S, int r) {
+    const std::vector<int64_t> u = universe_of(S);
+    if (u.empty()) { post_truth(r, false); return; }
+    for (size_t k = 0; k < u.size(); ++k) {
+      if (u[k] < lb[x] || u[k] > ub[x]) continue;             // x can never take this value
+      const int mv = tnf_var(S.elems[k]);
+      int e = fresh_bool(), c = fresh_bool();
+      prop(TB_OP_EQ, e, x, cst(u[k]));
+      prop(TB_OP_EQ, c, r, mv);
+      prop(TB_OP_LEQ, cst(1), e, c);
+    }
+    Expr uni; uni.kind = Expr::SET; uni.ranges = S.ranges;
+    int inside = fresh_bool();
+    set_in(x, uni, inside);
+    prop(TB_OP_LEQ, cst(1), r, inside);
+  }
+
+  // S = arr[idx], arr an array of constant sets: member_v = (idx in {k : v in arr[k]}); a set that leaves the universe
+  // cannot be selected
+  void set_element(int idx, const Expr& arr, const Expr& S) {
+    if (arr.kind != Expr::ARRAY || S.kind != Expr::SETVAR) throw std::runtime_error("array_set_element expects an array of constant sets and a set variable");
+    const std::vector<int64_t> u = universe_of(S);
+    restrict_lb(idx, 1); restrict_ub(idx, (int64_t)arr.elems.size());
+    for (size_t k = 0; k < arr.elems.size(); ++k) {
+      const Expr& sk = arr.elems[k];
+      if (sk.kind != Expr::SET) throw std::runtime_error("array_set_element: variable sets inside the array are not supported");
+      bool inside = true;
+      for (const auto& rg : sk.ranges) for (int64_t v = rg.first; v <= rg.second; ++v) inside = inside && set_has(S, v);
+      if (!inside) prop(TB_OP_EQ, cst(0), idx, cst((int64_t)k + 1));
+    }
+    for (size_t j = 0; j < u.size(); ++j) {
+      std::vector<int64_t> ks;
+      for (size_t k = 0; k < arr.elems.size(); ++k) if (set_has(arr.elems[k], u[j])) ks.push_back((int64_t)k + 1);
+      Expr K; K.kind = Expr::SET;
+      for (size_t i = 0; i < ks.size();) {
+        size_t e = i;
+        while (e + 1 < ks.size() && ks[e + 1] == ks[e] + 1) ++e;
+        K.ranges.push_back({ks[i], ks[e]});
+        i = e + 1;
+      }
+      set_in(idx, K, tnf_var(S.elems[j]));
+    }
+  }
+
   // r = op-fold(vs) for MIN (conjunction) / MAX (disjunction) over 0..1 variables
   void chain(int op, const std::vector<int>& vs, int r) {
     if (vs.empty()) { post_truth(r, op == TB_OP_MIN); return; }
@@ -356,8 +412,9 @@ struct Builder {
       need(3);
       element(tnf_var(a[0]), operands(a[1]), tnf_var(a[2]));
     }
-    else if (name == "set_in") { need(2); set_in(tnf_var(a[0]), a[1], ONE); }
-    else if (name == "set_in_reif") { need(3); set_in(tnf_var(a[0]), a[1], tnf_var(a[2])); }
+    else if (name == "set_in") { need(2); if (a[1].kind == Expr::SETVAR) set_in_var(tnf_var(a[0]), a[1], ONE); else set_in(tnf_var(a[0]), a[1], ONE); }
+    else if (name == "set_in_reif") { need(3); if (a[1].kind == Expr::SETVAR) set_in_var(tnf_var(a[0]), a[1], tnf_var(a[2])); else set_in(tnf_var(a[0]), a[1], tnf_var(a[2])); }
+    else if (name == "array_set_element") { need(3); set_element(tnf_var(a[0]), a[1], a[2]); }
     else throw std::runtime_error("unsupported FlatZinc constraint '" + name + "'");
   }
 };
@@ -489,6 +546,14 @@ struct Checker {
     for (size_t i = 0; i < cs.elems.size(); ++i) s += cs.elems[i].value * ev(xs.elems[i]);
     return s;
   }
+  bool in_set_var(int64_t x, const Expr& S) const {           // membership in a set variable at the point
+    size_t j = 0;
+    for (const auto& rg : S.ranges) {
+      if (x >= rg.first && x <= rg.second) return ev(S.elems[j + (size_t)(x - rg.first)]) != 0;
+      j += (size_t)(rg.second - rg.first + 1);
+    }
+    return false;
+  }
   static bool in_set(int64_t x, const Expr& s) {
     for (const auto& r : s.ranges) if (r.first <= x && x <= r.second) return true;
     return false;
@@ -536,7 +601,16 @@ struct Checker {
       if (i < 1 || i > (int64_t)a[1].elems.size()) return false;
       return ev(a[1].elems[(size_t)i - 1]) == ev(a[2]);
     }
-    if (name == "set_in") return in_set(ev(a[0]), a[1]);
+    if (name == "set_in") return a[1].kind == Expr::SETVAR ? in_set_var(ev(a[0]), a[1]) : in_set(ev(a[0]), a[1]);
+    if (name == "array_set_element") {
+      const int64_t i = ev(a[0]);
+      if (a[1].kind != Expr::ARRAY || a[2].kind != Expr::SETVAR || i < 1 || i > (int64_t)a[1].elems.size()) return false;
+      const Expr& sk = a[1].elems[(size_t)i - 1];
+      for (const auto& rg : sk.ranges) for (int64_t v = rg.first; v <= rg.second; ++v) if (!in_set_var(v, a[2])) return false;   // sk is a subset of S
+      size_t j = 0;
+      for (const auto& rg : a[2].ranges) for (int64_t v = rg.first; v <= rg.second; ++v, ++j) if ((ev(a[2].elems[j]) != 0) != in_set(v, sk)) return false;
+      return true;
+    }
     throw std::runtime_error("checker: unsupported constraint '" + name + "'");
   }
 };
