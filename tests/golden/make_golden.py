@@ -53,6 +53,8 @@ def main():
         dump(name, os.path.join("/root/reference", path), int(exp))
     for name in ("accap_a3", "trains15", "example_wordpress7_500"):
         dump(name, os.path.join(REF, name + ".fzn"), None)
+    for name in ("bigdom", "valve6"):            # unsolved_bugs_data: no expected answer; valve6 has set variables
+        dump(name, os.path.join(REF, "unsolved_bugs_data", name + ".fzn"), None)
 
 
 if __name__ == "__main__":

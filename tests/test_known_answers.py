@@ -19,7 +19,7 @@ BIG = {"trains15", "example_wordpress7_500"}
 
 
 def test_fixture_inventory():
-    assert len(WITH_ANSWER) == 32 and len(ALL) == 35
+    assert len(WITH_ANSWER) == 32 and len(ALL) == 37
 
 
 def sha_of(r):
@@ -41,7 +41,8 @@ def test_oracle_root_fixpoint_is_pinned(name):
 @pytest.mark.parametrize("name", ALL)
 def test_fixture_matches_fresh_frontend(name, reference_dir):
     from turbo_b200.model import Model
-    sub = "benchmarks" if name in BIG or name == "accap_a3" else "benchmarks/test_data"
+    sub = ("benchmarks" if name in BIG or name == "accap_a3" else
+           "benchmarks/unsolved_bugs_data" if name in ("bigdom", "valve6") else "benchmarks/test_data")
     m = Model.from_fzn(os.path.join(reference_dir, sub, name + ".fzn"))
     pb, info = golden_io.load(name)
     assert np.array_equal(m.problem.lb, pb.lb) and np.array_equal(m.problem.ub, pb.ub)
