@@ -299,3 +299,48 @@ def test_unsolved_bugs_valve6_goes_through_the_front_end(reference_dir):
     import os
     m = Model.from_fzn(os.path.join(reference_dir, "benchmarks", "unsolved_bugs_data", "valve6.fzn"))
     assert m.problem.nvars > 10000 and m.objective_kind == 1 and not m.root_failed
+
+
+# ---- half reification (_imp), bool_lin_*, array_int_minimum / maximum ---------------------------------------------------
+
+@pytest.mark.parametrize("seed", range(40))
+def test_imp_minmax_boollin_models_match_bruteforce(seed):
+    rng = np.random.default_rng(2000 + seed)
+    c = [int(v) for v in rng.integers(-3, 4, size=6)]
+    k1, k2, k3 = int(rng.integers(-2, 6)), int(rng.integers(0, 3)), int(rng.integers(-3, 6))
+    sense = "minimize" if rng.random() < 0.5 else "maximize"
+    which = "array_int_minimum" if rng.random() < 0.5 else "array_int_maximum"
+    text = "\n".join([
+        "var -2..3: x :: output_var;", "var -2..3: y :: output_var;", "var -2..3: z :: output_var;", "var -2..3: m :: output_var;",
+        "var bool: p :: output_var;", "var bool: q :: output_var;", "var 0..1: pi :: output_var;", "var 0..1: qi :: output_var;",
+        "var -60..60: obj :: output_var;",
+        f"constraint {which}(m, [x, y, z]);",
+        f"constraint int_lin_le_imp([{c[0]},{c[1]}],[x,y],{k1},p);",
+        f"constraint int_eq_imp(y, z, q);",
+        f"constraint bool_lin_le([1,1],[p,q],{k2});",
+        f"constraint bool_clause_imp([p],[q],q);",
+        "constraint bool2int(p, pi);", "constraint bool2int(q, qi);",
+        f"constraint int_lin_le([{c[2]},{c[3]}],[x,z],{k3});",
+        f"constraint int_lin_eq([{c[4]},{c[5]},2,3,-2,-1],[x,m,pi,qi,z,obj],0);",
+        f"solve {sense} obj;"])
+    best = None
+    import itertools
+    for x, y, z, p, q in itertools.product(range(-2, 4), range(-2, 4), range(-2, 4), (0, 1), (0, 1)):
+        m = min(x, y, z) if which == "array_int_minimum" else max(x, y, z)
+        if p and not (c[0] * x + c[1] * y <= k1): continue
+        if q and not (y == z): continue
+        if p + q > k2: continue
+        if q and not (p or not q): continue          # q -> (p \\/ not q)
+        if c[2] * x + c[3] * z > k3: continue
+        obj = c[4] * x + c[5] * m + 2 * p + 3 * q - 2 * z
+        if best is None or (obj < best if sense == "minimize" else obj > best):
+            best = obj
+    mdl = Model.from_fzn_text(text)
+    if mdl.root_failed:
+        assert best is None, text
+        return
+    r = orc.solve(mdl.problem, depth=2)
+    assert r["exhaustive"] and r["has_solution"] == (best is not None), text
+    if best is not None:
+        assert mdl.user_objective(r["lb"], r["ub"]) == best, text
+        assert mdl.check_solution(r["lb"]) == 0, text

@@ -345,6 +345,35 @@ struct Builder {
   void post(const std::string& name, const std::vector<Expr>& a) {
     auto need = [&](size_t n) { if (a.size() != n) throw std::runtime_error("constraint " + name + " expects " + std::to_string(n) + " arguments"); };
     const int ONE = cst(1), ZERO = cst(0);
+    // half reification  r -> C  (the _imp predicates of recent MiniZinc): r <= r' with r' <-> C
+    if (name.size() > 4 && name.compare(name.size() - 4, 4, "_imp") == 0 && !a.empty()) {
+      const int r = tnf_var(a.back());
+      const int full = fresh_bool();
+      std::vector<Expr> args(a.begin(), a.end() - 1);
+      Expr re; re.kind = Expr::VAR; re.var = -1 - full;      // negative: already a TNF variable
+      args.push_back(re);
+      post(name.substr(0, name.size() - 4) + "_reif", args);
+      prop(TB_OP_LEQ, ONE, r, full);
+      return;
+    }
+    if (name == "bool_lin_eq" || name == "bool_lin_le") { post(name == "bool_lin_eq" ? "int_lin_eq" : "int_lin_le", a); return; }
+    if (name == "array_int_minimum" || name == "array_int_maximum") {
+      need(2);
+      std::vector<int> vs = operands(a[1]);
+      if (vs.empty()) throw std::runtime_error(name + " over an empty array");
+      const int op = name == "array_int_minimum" ? TB_OP_MIN : TB_OP_MAX;
+      const int m = tnf_var(a[0]);
+      if (vs.size() == 1) { prop(TB_OP_EQ, ONE, m, vs[0]); return; }
+      int acc = vs[0];
+      for (size_t i = 1; i < vs.size(); ++i) {
+        int64_t l = op == TB_OP_MIN ? std::min(lb[acc], lb[vs[i]]) : std::max(lb[acc], lb[vs[i]]);
+        int64_t u = op == TB_OP_MIN ? std::min(ub[acc], ub[vs[i]]) : std::max(ub[acc], ub[vs[i]]);
+        const int nx = i + 1 == vs.size() ? m : fresh(l, u);
+        prop(op, nx, acc, vs[i]);
+        acc = nx;
+      }
+      return;
+    }
     if (name == "int_lin_le") { need(3); lin_le(terms(a[0], a[1]), int_of(a[2]), ONE); }
     else if (name == "int_lin_le_reif") { need(4); lin_le(terms(a[0], a[1]), int_of(a[2]), tnf_var(a[3])); }
     else if (name == "int_lin_eq") { need(3); lin_eq(terms(a[0], a[1]), int_of(a[2]), ONE); }
@@ -561,6 +590,17 @@ struct Checker {
 
   bool holds(const std::string& name, const std::vector<Expr>& a) const {
     const size_t n = a.size();
+    if (name.size() > 4 && name.compare(name.size() - 4, 4, "_imp") == 0) {       // r -> C
+      std::vector<Expr> base(a.begin(), a.end() - 1);
+      return ev(a[n - 1]) == 0 || holds(name.substr(0, name.size() - 4), base);
+    }
+    if (name == "bool_lin_eq") return dot(a[0], a[1]) == a[2].value;
+    if (name == "bool_lin_le") return dot(a[0], a[1]) <= a[2].value;
+    if (name == "array_int_minimum" || name == "array_int_maximum") {
+      std::vector<int64_t> vs = evs(a[1]);
+      if (vs.empty()) return false;
+      return ev(a[0]) == (name == "array_int_minimum" ? *std::min_element(vs.begin(), vs.end()) : *std::max_element(vs.begin(), vs.end()));
+    }
     if (name.size() > 5 && name.compare(name.size() - 5, 5, "_reif") == 0) {
       std::vector<Expr> base(a.begin(), a.end() - 1);
       return holds(name.substr(0, name.size() - 5), base) == (ev(a[n - 1]) != 0);
