@@ -109,6 +109,15 @@ def reduce_over_ranks(dist, sums, maxes, device="cpu"):
     return [float(x) for x in t.tolist()], [float(x) for x in m.tolist()]
 
 
+def workload_name(workload):
+    """BASELINE.json's wording for the configuration: config 2 is `benchmarks/trains15.fzn optimisation, gpu dive-and-solve`."""
+    if workload.startswith("synthetic"):
+        return "synthetic random TNF constraint network (BASELINE config 5)"
+    simplified = workload.startswith("simplified:")
+    name = workload.split(":", 1)[1] if simplified else workload
+    return "benchmarks/%s.fzn optimisation, gpu dive-and-solve (%s)" % (name, "TNF after the simplifier, the driver's default" if simplified else "TNF as with -disable_simplify")
+
+
 def data_description(workload):
     if workload.startswith("synthetic"):
         return "synthetic"
@@ -259,7 +268,8 @@ def run_ours(args):
             "metric": "propagations/sec", "value": ded / secs if secs > 0 else 0.0, "unit": "propagations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": data_description(args.workload),
-            "config": {"workload": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "cutnodes_per_block": args.cutnodes,
+            "config": {"workload": workload_name(args.workload), "workload_arg": args.workload, "nvars": pb.nvars, "nprops": pb.nprops,
+                       "cutnodes_per_block": args.cutnodes,
                        "fixpoint": args.fp, "num_blocks_per_gpu": cfg["num_blocks"], "threads_per_block": cfg["threads_per_block"],
                        "memory_configuration": abi.MEM_NAMES.get(cfg["mem_kind"], "?"), "subproblems_power": cfg["subproblems_power"],
                        "l2": "flushed between steps (256 MiB write)", "parallelism": f"eps-shard x{world}"},
@@ -347,7 +357,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": data_description(args.workload),
-            "config": {"workload": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "step": f"{budget_ms} ms of CPU dive-and-solve"},
+            "config": {"workload": workload_name(args.workload), "workload_arg": args.workload, "nvars": pb.nvars, "nprops": pb.nprops, "step": f"{budget_ms} ms of CPU dive-and-solve"},
             "nodes_per_sec": nodes / secs,
             "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} x {budget_ms} ms of oracle dive-and-solve, EPS over {cores} threads"},

@@ -24,7 +24,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["nodes_per_sec"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == "simplified:accap_a3"
+    assert d["config"]["workload_arg"] == "simplified:accap_a3" and "benchmarks/accap_a3.fzn" in d["config"]["workload"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
