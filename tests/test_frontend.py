@@ -344,3 +344,18 @@ def test_imp_minmax_boollin_models_match_bruteforce(seed):
     if best is not None:
         assert mdl.user_objective(r["lb"], r["ub"]) == best, text
         assert mdl.check_solution(r["lb"]) == 0, text
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_int_pow_with_a_constant_exponent(k):
+    for sense in ("minimize", "maximize"):
+        text = (f"var -3..3: x :: output_var;\nvar -30..30: z :: output_var;\nvar -40..40: obj :: output_var;\n"
+                f"constraint int_pow(x, {k}, z);\nconstraint int_lin_eq([1,-2,-1],[z,x,obj],0);\nsolve {sense} obj;\n")
+        vals = [x ** k - 2 * x for x in range(-3, 4) if -30 <= x ** k <= 30]
+        m = Model.from_fzn_text(text)
+        r = orc.solve(m.problem, depth=1)
+        assert r["has_solution"] and r["exhaustive"]
+        assert m.user_objective(r["lb"], r["ub"]) == (min(vals) if sense == "minimize" else max(vals))
+        assert m.check_solution(r["lb"]) == 0
+    with pytest.raises(Exception):
+        Model.from_fzn_text("var 0..3: x;\nvar 0..3: y;\nvar 0..30: z;\nconstraint int_pow(x, y, z);\nsolve satisfy;\n")

@@ -13,6 +13,14 @@ namespace {
 constexpr int64_t NINF = TB_NEG_INF, PINF = TB_POS_INF;
 
 int64_t sat(int64_t v) { return v <= NINF ? NINF : (v >= PINF ? PINF : v); }
+// product of two bounds that may be infinite (0 * oo = 0: the other factor is exactly 0)
+int64_t sat_mul(int64_t a, int64_t b) {
+  if (a == 0 || b == 0) return 0;
+  const bool neg = (a < 0) != (b < 0);
+  if (a == NINF || a == PINF || b == NINF || b == PINF) return neg ? NINF : PINF;
+  const __int128 p = (__int128)a * (__int128)b;
+  return p <= (__int128)NINF ? NINF : (p >= (__int128)PINF ? PINF : (int64_t)p);
+}
 bool is_inf(int64_t v) { return v == NINF || v == PINF; }
 int64_t fdiv(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
 int64_t cdiv(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) == (b < 0))) ? q + 1 : q; }
@@ -356,6 +364,26 @@ struct Builder {
       prop(TB_OP_LEQ, ONE, r, full);
       return;
     }
+    if (name == "int_pow") {          // z = x ^ k for a constant exponent k >= 0: a chain of multiplications
+      need(3);
+      if (a[1].kind != Expr::INT || a[1].value < 0 || a[1].value > 30) throw std::runtime_error("int_pow needs a constant exponent in 0..30");
+      const int x = tnf_var(a[0]), z = tnf_var(a[2]);
+      const int64_t k = a[1].value;
+      if (k == 0) { prop(TB_OP_EQ, ONE, z, ONE); return; }
+      if (k == 1) { prop(TB_OP_EQ, ONE, z, x); return; }
+      int acc = x;
+      for (int64_t i = 2; i <= k; ++i) {
+        int64_t l, u; 
+        {   // bounds of acc * x from the corner products (saturating)
+          const int64_t c[4] = {sat_mul(lb[acc], lb[x]), sat_mul(lb[acc], ub[x]), sat_mul(ub[acc], lb[x]), sat_mul(ub[acc], ub[x])};
+          l = *std::min_element(c, c + 4); u = *std::max_element(c, c + 4);
+        }
+        const int nx = i == k ? z : fresh(l, u);
+        prop(TB_OP_MUL, nx, acc, x);
+        acc = nx;
+      }
+      return;
+    }
     if (name == "bool_lin_eq" || name == "bool_lin_le") { post(name == "bool_lin_eq" ? "int_lin_eq" : "int_lin_le", a); return; }
     if (name == "array_int_minimum" || name == "array_int_maximum") {
       need(2);
@@ -593,6 +621,11 @@ struct Checker {
     if (name.size() > 4 && name.compare(name.size() - 4, 4, "_imp") == 0) {       // r -> C
       std::vector<Expr> base(a.begin(), a.end() - 1);
       return ev(a[n - 1]) == 0 || holds(name.substr(0, name.size() - 4), base);
+    }
+    if (name == "int_pow") {
+      int64_t r = 1;
+      for (int64_t i = 0; i < ev(a[1]); ++i) r *= ev(a[0]);
+      return ev(a[1]) >= 0 && r == ev(a[2]);
     }
     if (name == "bool_lin_eq") return dot(a[0], a[1]) == a[2].value;
     if (name == "bool_lin_le") return dot(a[0], a[1]) <= a[2].value;
