@@ -179,3 +179,29 @@ def test_satisfaction_problems_and_strategies_after_simplification():
     vals = dict(line.rstrip(";").split(" = ") for line in m.format_solution(r["lb"]).strip().splitlines())
     a, b, c, d = (int(vals[k]) for k in "abcd")
     assert len({a, b, c}) == 3 and c == d and a + b <= 4 and a <= b
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_tnf_networks_keep_status_and_optimum(seed, tmp_path):
+    """Every operator (MUL, TDIV, TMOD, MIN, MAX, EQ, LEQ, ADD) on small random networks, straight at the TNF level: the
+    reduced network has the same satisfiability and the same optimum as the full one, and its solutions expand to points
+    that satisfy every original propagator."""
+    from oracle import oracle_py as orc
+    from tests import tnf_gen
+    pb = tnf_gen.search_instance(seed // 3 % 12) if seed % 3 == 0 else tnf_gen.random_net(14, 9, 7000 + seed, lo=-4, hi=4)
+    o = orc.solve(pb, depth=0, timeout_ms=60000)
+    info = dict(objective_kind=0 if pb.obj_var >= 0 else -1, user_obj_var=pb.obj_var)
+    path = str(tmp_path / "net.tnf")
+    golden_io.write_tnf(path, pb, info)
+    m = Model.from_tnf(path)
+    m.simplify(oracle_fixpoint)
+    if m.root_failed:
+        assert not o["has_solution"]
+        return
+    r = orc.solve(m.problem, depth=0, timeout_ms=60000)
+    assert r["exhaustive"] and o["exhaustive"]
+    assert r["has_solution"] == o["has_solution"], seed
+    if o["has_solution"]:
+        if pb.obj_var >= 0:
+            assert m.user_objective(r["lb"], r["ub"]) == o["objective"], seed
+        assert m.check_tnf(r["lb"]) == 0, seed
