@@ -114,6 +114,8 @@ typedef struct {
   int64_t cumulative_time_block_ns;
   int64_t timers_ns[TB_NUM_TIMERS];
   double kernel_ms;               /* device time of the solve kernel (CUDA events on its stream) */
+  uint64_t eps_stolen_subproblems; /* subproblems this GPU took from a peer's shard once its own was exhausted */
+  uint64_t device_bytes;          /* device memory the solver holds (the reference's heap_memory, barebones :579) */
 } tb_stats;
 
 typedef enum { TB_OK = 0, TB_ERR_INVALID = 1, TB_ERR_CUDA = 2, TB_ERR_NOMEM = 3, TB_ERR_UNSUPPORTED = 4,
@@ -158,13 +160,22 @@ tb_status tb_solve(tb_solver*, volatile int32_t* stop_flag,
                    int32_t* best_lb, int32_t* best_ub, int32_t* has_solution,
                    int32_t* exhaustive, tb_stats* stats);
 
-/* Cross-GPU incumbent sharing.  Each solver owns one device int32 incumbent cell.
- * Same process: link solvers living on different devices (peer access is enabled here).
- * Other processes (one rank per GPU): export a 64-byte CUDA IPC handle and import the peers'. */
+/* Cross-GPU incumbent sharing and work stealing (GridData::appx_best_bound / next_subproblem,
+ * barebones_dive_and_solve.hpp:418,426, which the reference keeps on one device).  Each solver owns one 128-byte
+ * block of device cells: its incumbent, the dispenser of its shard (idx = k * gpu_world + gpu_rank) and a stop
+ * word.  Linked solvers map each other's blocks over NVLink: an improving block writes the incumbent to every
+ * GPU with a system-scope atomicMin, a GPU whose shard is exhausted takes subproblems from a peer's dispenser
+ * (TB_STEAL=0 keeps the shards static), the first solution of a satisfaction problem stops every GPU.
+ * Same process: tb_link_peers on solvers living on different devices (peer access is enabled here).
+ * Other processes (one rank per GPU): export a 64-byte CUDA IPC handle and import the peers' handles IN RANK
+ * ORDER WITH THE OWN RANK LEFT OUT (npeers = gpu_world - 1).
+ * Runs: every tb_solve call of a solver starts a new epoch, and every cell value carries the epoch it belongs to,
+ * so nothing has to be reset between runs and a write of a peer that is still in (or already past) another run is
+ * ignored.  The one requirement: linked solvers make the same sequence of tb_solve calls. */
 tb_status tb_link_peers(tb_solver** solvers, int32_t n);
 tb_status tb_export_bound_handle(tb_solver*, void* handle64);
 tb_status tb_import_peer_bounds(tb_solver*, const void* handles64, int32_t npeers);
-/* Current value of this solver's incumbent cell (TB_POS_INF when none). */
+/* Incumbent of this solver's latest run as its own cell holds it (TB_POS_INF when none). */
 tb_status tb_read_bound(tb_solver*, int32_t* bound);
 
 /* Fills `stats` with the launch configuration chosen by tb_create (num_blocks, mem_kind, ...). */
@@ -194,6 +205,16 @@ const char* tb_last_error(void);
 const char* tb_version(void);
 /* Number of visible CUDA devices, or 0. Never fails. */
 int32_t tb_device_count(void);
+/* What the reference prints about the device (cuda_version: include/config.hpp:258-260; total_global_mem_bytes,
+ * heap_memory, stack_memory: barebones_dive_and_solve.hpp:579-593). */
+typedef struct {
+  int32_t cuda_runtime_version, cuda_driver_version, sm_count, cc_major, cc_minor, pad_;
+  uint64_t total_global_mem_bytes, free_global_mem_bytes, stack_limit_bytes, heap_limit_bytes;
+  char name[64];
+} tb_device_info;
+tb_status tb_get_device_info(int32_t device, tb_device_info* info);
+/* -stack <KB>: per-thread stack limit of the device (cudaLimitStackSize, barebones :588-593). */
+tb_status tb_set_stack_limit(int32_t device, uint64_t bytes);
 
 /* ---- host front-end (C++ behind a C surface) ------------------------------------------------- */
 

@@ -72,7 +72,8 @@ class TbStats(C.Structure):
                 ("shared_bytes", C.c_uint64), ("store_bytes", C.c_uint64), ("prop_bytes", C.c_uint64),
                 ("cumulative_time_block_ns", C.c_int64),
                 ("timers_ns", C.c_int64 * NUM_TIMERS),
-                ("kernel_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("eps_stolen_subproblems", C.c_uint64),
+                ("device_bytes", C.c_uint64)]
 
     def as_dict(self):
         d = {}
@@ -80,6 +81,13 @@ class TbStats(C.Structure):
             v = getattr(self, name)
             d[name] = list(v) if name == "timers_ns" else v
         return d
+
+
+class TbDeviceInfo(C.Structure):
+    _fields_ = [("cuda_runtime_version", C.c_int32), ("cuda_driver_version", C.c_int32), ("sm_count", C.c_int32),
+                ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("pad_", C.c_int32),
+                ("total_global_mem_bytes", C.c_uint64), ("free_global_mem_bytes", C.c_uint64),
+                ("stack_limit_bytes", C.c_uint64), ("heap_limit_bytes", C.c_uint64), ("name", C.c_char * 64)]
 
 
 class TbSimplifyStats(C.Structure):

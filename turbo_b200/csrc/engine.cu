@@ -98,7 +98,8 @@ __device__ __forceinline__ void bulk_commit_wait_all() {
 struct Ctl {                       // per-CTA control block in static shared memory
   unsigned long long mbar;
   unsigned long long sel_key;      // arg-min key of the variable selection
-  unsigned long long subproblem_k; // local subproblem counter value being solved
+  unsigned long long subproblem_k; // counter value of the subproblem being solved: idx = subproblem_k * world + sub_owner
+  int sub_owner;                   // the rank whose shard it comes from (this GPU's, or a peer's when it was stolen)
   int flags[3];                    // rotating fixpoint flag words
   int sel_first;
   int stop, leaf, failed;
@@ -252,6 +253,70 @@ struct Ctx {
     } else __syncthreads();
   }
 
+  // ---- grid cells (engine_internal.h): incumbent, dispenser, stop; thread 0 only -----------------
+  __device__ __forceinline__ unsigned long long bound_word(int b) const {
+    return ((unsigned long long)(~P.epoch) << 32) | (unsigned long long)((unsigned)b ^ 0x80000000u);
+  }
+  // GridData::appx_best_bound (:426): this GPU's copy; a word left by another run reads as "no incumbent"
+  __device__ __forceinline__ int read_bound() const {
+    const unsigned long long v = *(volatile unsigned long long*)(P.cells + TB_CELL_BOUND);
+    return (unsigned)(v >> 32) == ~P.epoch ? (int)((unsigned)v ^ 0x80000000u) : TBD_PINF;
+  }
+  // an improving solution goes to this GPU's cell and to every peer's over NVLink (:997 + SURVEY 8e)
+  __device__ __forceinline__ void publish_bound(int l) const {
+    const unsigned long long w = bound_word(l);
+    atomicMin(P.cells + TB_CELL_BOUND, w);
+    for (int g = 0; g < P.npeers; ++g) atomicMin_system(P.peer_cells[g] + TB_CELL_BOUND, w);
+  }
+  __device__ __forceinline__ bool stop_raised() const {
+    if (!P.observe_stop) return false;
+    volatile int* f = (volatile int*)(P.cells + TB_CELL_STOP);
+    return f[0] == (int)P.epoch || f[1] != 0;
+  }
+  // everywhere: the whole job is over (first solution of a satisfaction problem, unbounded objective)
+  __device__ __forceinline__ void raise_stop(bool everywhere) const {
+    if (!P.observe_stop) return;
+    *(volatile int*)(P.cells + TB_CELL_STOP) = (int)P.epoch;
+    if (everywhere) for (int g = 0; g < P.npeers; ++g) *(volatile int*)(P.peer_cells[g] + TB_CELL_STOP) = (int)P.epoch;
+  }
+  // Monotone max on the dispenser of rank q's shard: nobody hands out a counter value below k any more (subtree skip,
+  // :732-734). The own cell always carries this run's epoch; a peer's may belong to another run and is left alone then.
+  __device__ __forceinline__ void dispenser_skip_to(int peer, unsigned long long k) const {
+    const unsigned long long tag = (unsigned long long)P.epoch << TB_K_BITS;
+    if (peer < 0) { atomicMax(P.cells + TB_CELL_NEXT, tag | k); return; }
+    unsigned long long* cell = P.peer_cells[peer] + TB_CELL_NEXT;
+    unsigned long long v = *(volatile unsigned long long*)cell;
+    while ((v >> TB_K_BITS) == (unsigned long long)P.epoch && (v & TB_K_MASK) < k) {
+      const unsigned long long old = atomicCAS_system(cell, v, tag | k);
+      if (old == v) break;
+      v = old;
+    }
+  }
+  // G (:873-885) generalised to several GPUs: the next subproblem of this GPU's shard, or, once that is exhausted, of a
+  // peer's shard (work stealing through the peer-mapped dispensers; a CAS, so that a dispenser of another run is never
+  // advanced). Sets c.subproblem_k / c.sub_owner; an exhausted value (idx >= num_subproblems) ends the block.
+  __device__ __forceinline__ void next_subproblem() {
+    const unsigned long long world = (unsigned long long)P.world;
+    unsigned long long k = atomicAdd(P.cells + TB_CELL_NEXT, 1ull) & TB_K_MASK;
+    int owner = P.rank;
+    if (k * world + (unsigned long long)P.rank >= P.num_subproblems && P.steal) {
+      for (int t = 0; t < P.npeers; ++t) {
+        const int g = (slot + t) % P.npeers;
+        unsigned long long* cell = P.peer_cells[g] + TB_CELL_NEXT;
+        unsigned long long v = *(volatile unsigned long long*)cell;
+        bool got = false;
+        while ((v >> TB_K_BITS) == (unsigned long long)P.epoch &&
+               (v & TB_K_MASK) * world + (unsigned long long)P.peer_rank[g] < P.num_subproblems) {
+          const unsigned long long old = atomicCAS_system(cell, v, v + 1ull);
+          if (old == v) { got = true; break; }
+          v = old;
+        }
+        if (got) { k = v & TB_K_MASK; owner = P.peer_rank[g]; st->eps_stolen += 1; break; }
+      }
+    }
+    c.subproblem_k = k; c.sub_owner = owner;
+  }
+
   // ---- copies between the block store and a global image of it ---------------------------------
   // An image is P.vpad * 8 bytes; with a cluster it is C slices of vc * 8 bytes, one per CTA, and every
   // CTA moves its own slice with its own mbarrier.
@@ -326,7 +391,7 @@ struct Ctx {
   };
 
   // A chunk's words are requested at the end of the visit before the previous one. The global table is followed
-  // by 160 chunks of padding, so the prefetch needs no bound check; the shared copy (TCN_SHARED) is not, and clamps.
+  // by 2 * nwarps + 1 chunks of padding (tb_create), so the prefetch needs no bound check; the shared copy (TCN_SHARED) is not, and clamps.
   __device__ __forceinline__ Words load_words(const unsigned long long* words, int i) const {
     Words r;
     if (MEM == TB_MEM_TCN_SHARED) i = min(i, (P.nchunks * 32 - 1) * TBC_U);
@@ -630,8 +695,7 @@ struct Ctx {
         sync();
         if (improved && tid == 0) {
           c.best_bound = l;
-          atomicMin(P.appx_best_bound, l);
-          for (int g = 0; g < P.npeers; ++g) atomicMin_system(P.peer_bounds[g], l);
+          publish_bound(l);
           st->t_best = (long long)(globaltimer_ns() - P.t_start);
           st->best_bound = l;
         }
@@ -656,9 +720,9 @@ struct Ctx {
       if (solution && P.obj_var < 0) {       // satisfaction: stop everybody after the first solution
         st->exhaustive = 0;
         c.stop = 1;
-        *P.stop = 1;
+        raise_stop(true);
       }
-      if ((P.cutnodes && st->nodes >= P.cutnodes) || *P.stop) {
+      if ((P.cutnodes && st->nodes >= P.cutnodes) || stop_raised()) {
         st->exhaustive = 0;
         c.stop = 1;
       }
@@ -681,7 +745,7 @@ struct Ctx {
 
   // thread 0 only
   __device__ __forceinline__ void push_decision(int val_order, int var) {
-    if (c.depth >= P.max_depth) { st->error = TB_ERR_DEPTH; st->exhaustive = 0; c.stop = 1; *P.stop = 1; c.pushed = 0; return; }
+    if (c.depth >= P.max_depth) { st->error = TB_ERR_DEPTH; st->exhaustive = 0; c.stop = 1; raise_stop(false); c.pushed = 0; return; }
     int l, u; store.ld(var, l, u);
     Decision d;
     d.var = var; d.cur = -1;
@@ -796,7 +860,7 @@ struct Ctx {
     int mode = M_START;
     for (;;) {
       if (mode == M_START) {
-        idx = c.subproblem_k * world + rank;     // this GPU's shard: idx = rank (mod world)
+        idx = c.subproblem_k * world + (unsigned long long)c.sub_owner;     // a shard is idx = owner (mod world)
         if (idx >= nsub || c.stop) break;
         sync();
         if (tid == 0) {
@@ -817,9 +881,13 @@ struct Ctx {
         if (c.leaf && !c.stop) {
           // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
           if (tid == 0) {
-            unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
-            unsigned long long next_k = next <= rank ? 0ull : (next - rank + world - 1ull) / world;
-            atomicMax(P.next_subproblem, next_k);
+            // nobody needs to dive into [idx, next) any more: advance every shard's dispenser past it
+            const unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
+            dispenser_skip_to(-1, next <= rank ? 0ull : (next - rank + world - 1ull) / world);
+            for (int g = 0; g < P.npeers && P.steal; ++g) {
+              const unsigned long long q = (unsigned long long)P.peer_rank[g];
+              dispenser_skip_to(g, next <= q ? 0ull : (next - q + world - 1ull) / world);
+            }
             if ((idx & ((1ull << remaining) - 1ull)) == 0ull) st->eps_skipped += next - idx;
           }
           mode = M_NEXT;
@@ -834,13 +902,13 @@ struct Ctx {
         else {
           // I. inject the incumbent bound (thread 0), detect an unconstrained objective
           if (tid == 0 && P.obj_var >= 0) {
-            int appx = *(volatile int*)P.appx_best_bound;
+            int appx = read_bound();
             if (appx != TBD_PINF) {
               bool moved = store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
               moved |= store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
               if (moved) mark_var(P.obj_var);
             }
-            if (appx == TBD_NINF) { c.stop = 1; *P.stop = 1; }
+            if (appx == TBD_NINF) { c.stop = 1; raise_stop(true); }
           }
           sync();
           if (c.stop) mode = M_SOLVE_END;
@@ -848,12 +916,12 @@ struct Ctx {
       }
       if (mode == M_SOLVE_END) {
         sync();
-        if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->eps_solved += 1;
+        if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !stop_raised()) st->eps_solved += 1;
         mode = M_NEXT;
       }
       if (mode == M_NEXT) {
         sync();
-        if (tid == 0 && !c.stop) c.subproblem_k = atomicAdd(P.next_subproblem, 1ull);
+        if (tid == 0 && !c.stop) next_subproblem();
         sync();
         mode = M_START;
         continue;
@@ -1057,11 +1125,15 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid;
   BlockStats* st = k.st;
-  if (tid == 0) c.subproblem_k = (unsigned long long)k.slot;
+  if (tid == 0) {
+    c.subproblem_k = (unsigned long long)k.slot; c.sub_owner = P.rank;
+    // this run's epoch enters the incumbent cell: whatever an earlier run (of this solver or of a peer) left is void
+    atomicMin(P.cells + TB_CELL_BOUND, k.bound_word(TBD_PINF));
+  }
   k.sync();
   k.search();
   if (tid == 0) {
-    if (!(P.cutnodes && st->nodes >= P.cutnodes) && !*P.stop) st->blocks_done = 1;
+    if (!(P.cutnodes && st->nodes >= P.cutnodes) && !k.stop_raised()) st->blocks_done = 1;
     st->t_idle = (long long)(globaltimer_ns() - P.t_start);
   }
   ctx_finish(k);
@@ -1165,6 +1237,40 @@ extern "C" int32_t tb_device_count(void) {
   return n;
 }
 
+extern "C" tb_status tb_get_device_info(int32_t device, tb_device_info* info) {
+  if (!info) { set_error("null argument"); return TB_ERR_INVALID; }
+  memset(info, 0, sizeof(*info));
+  if (tb_device_count() <= device || device < 0) { set_error("no such CUDA device"); return TB_ERR_NO_DEVICE; }
+  cudaDeviceProp dp;
+  CU(cudaGetDeviceProperties(&dp, device));
+  CU(cudaRuntimeGetVersion(&info->cuda_runtime_version));
+  CU(cudaDriverGetVersion(&info->cuda_driver_version));
+  info->sm_count = dp.multiProcessorCount; info->cc_major = dp.major; info->cc_minor = dp.minor;
+  info->total_global_mem_bytes = dp.totalGlobalMem;
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  CU(cudaSetDevice(device));
+  size_t fr = 0, tot = 0, lim = 0;
+  if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) info->free_global_mem_bytes = fr;
+  if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess) info->stack_limit_bytes = lim;
+  if (cudaDeviceGetLimit(&lim, cudaLimitMallocHeapSize) == cudaSuccess) info->heap_limit_bytes = lim;
+  cudaGetLastError();
+  cudaSetDevice(prev);
+  strncpy(info->name, dp.name, sizeof(info->name) - 1);
+  return TB_OK;
+}
+
+extern "C" tb_status tb_set_stack_limit(int32_t device, uint64_t bytes) {
+  if (tb_device_count() <= device || device < 0) { set_error("no such CUDA device"); return TB_ERR_NO_DEVICE; }
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  CU(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceSetLimit(cudaLimitStackSize, (size_t)bytes);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) { set_error(std::string("cudaDeviceSetLimit(stack): ") + cudaGetErrorString(e)); cudaGetLastError(); return TB_ERR_CUDA; }
+  return TB_OK;
+}
+
 struct tb_solver {
   DevParams P;
   tb_options opt;
@@ -1176,15 +1282,15 @@ struct tb_solver {
   size_t shared_bytes = 0, store_bytes = 0, prop_bytes = 0;
   bool want_active = false, active = false;   // TB_FP_*_ACTIVE requested / in effect (shared-memory placements)
   int num_sms = 0;
+  size_t device_bytes = 0;            // what the solver holds on the device
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   std::vector<void*> allocs;
-  std::vector<int*> peer_cells;       // device pointers to other GPUs' incumbent cells
+  std::vector<unsigned long long*> peer_cells;   // device pointers to the other GPUs' cell blocks (engine_internal.h)
+  std::vector<int> peer_ranks;        // the shard (gpu_rank) each of them dispenses
   std::vector<void*> ipc_opened;
-  int** d_peer_array = nullptr;
-  int* d_bound = nullptr;
-  int* d_stop = nullptr;
-  unsigned long long* d_next = nullptr;
+  unsigned long long* d_cells = nullptr;   // this GPU's cell block: incumbent, dispenser, stop
+  unsigned epoch = 0;                 // number of tb_solve calls so far: tags the cells of the current run
   int scratch_blocks = 0;             // number of per-block scratch slots allocated
   // batch buffers (grown on demand)
   int *d_in_lb = nullptr, *d_in_ub = nullptr, *d_out_lb = nullptr, *d_out_ub = nullptr, *d_out_i0 = nullptr, *d_out_i1 = nullptr;
@@ -1216,6 +1322,7 @@ static tb_status dev_alloc(tb_solver* s, T** p, size_t count) {
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);   // usable from the solver's own streams
   if (e != cudaSuccess) { set_error(std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TB_ERR_NOMEM : TB_ERR_CUDA; }
   s->allocs.push_back(q);
+  s->device_bytes += bytes;
   *p = (T*)q;
   return TB_OK;
 }
@@ -1557,9 +1664,12 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   {
     const TnfLayout& L = s->layout;
     unsigned long long* d = nullptr;
-    // 160 chunks of padding behind the table: a warp prefetches up to five visits ahead without a bound check
-    if ((rc = dev_alloc(s, &d, L.words.size() + 160 * 32 * TBC_U))) return fail(rc);
-    if (cudaMemset(d, 0, (L.words.size() + 160 * 32 * TBC_U) * 8) != cudaSuccess ||
+    // Padding behind the table: a warp requests the words of the chunks two visits ahead (ch + 2 * nwarps) without a bound
+    // check, so 2 * nwarps + 1 chunks past the end are read (never used). nwarps is the warp count of a whole worker:
+    // threads * cluster / 32, up to 512 with a cluster of 16.
+    const size_t pad_words = (size_t)(2 * (s->threads * std::max(1, s->cluster) / 32) + 1) * 32 * TBC_U;
+    if ((rc = dev_alloc(s, &d, L.words.size() + pad_words))) return fail(rc);
+    if (cudaMemset(d, 0, (L.words.size() + pad_words) * 8) != cudaSuccess ||
         (L.words.size() && cudaMemcpy(d, L.words.data(), L.words.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)) { set_error("H2D props"); return fail(TB_ERR_CUDA); }
     P.words = d;
     if (s->active) {
@@ -1611,12 +1721,16 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (cudaMemcpy(d, hs.data(), hs.size() * sizeof(DevStrategy), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D strategies"); return fail(TB_ERR_CUDA); }
     P.strategies = d; P.nstrategies = pb->nstrategies;
   }
-  // the incumbent cell is exported to other processes (CUDA IPC): that needs a plain cudaMalloc allocation
-  if (cudaMalloc((void**)&s->d_bound, 128) != cudaSuccess) { set_error("cudaMalloc (incumbent cell) failed"); cudaGetLastError(); return fail(TB_ERR_CUDA); }
-  if ((rc = dev_alloc(s, &s->d_stop, 32))) return fail(rc);
-  if ((rc = dev_alloc(s, &s->d_next, 4))) return fail(rc);
-  P.appx_best_bound = s->d_bound; P.stop = s->d_stop; P.next_subproblem = s->d_next;
-  P.peer_bounds = nullptr; P.npeers = 0;
+  // the cell block is exported to other processes (CUDA IPC): that needs a plain cudaMalloc allocation
+  {
+    unsigned long long init[TB_CELL_WORDS] = {0};
+    init[TB_CELL_BOUND] = ~0ull;            // epoch 0, no incumbent
+    if (cudaMalloc((void**)&s->d_cells, sizeof(init)) != cudaSuccess ||
+        cudaMemcpy(s->d_cells, init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("cudaMalloc (grid cells) failed"); cudaGetLastError(); return fail(TB_ERR_CUDA);
+    }
+  }
+  P.cells = s->d_cells; P.npeers = 0; P.steal = 0; P.epoch = 0; P.observe_stop = 1;
   if ((rc = ensure_scratch(s, s->num_blocks))) return fail(rc);
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1632,7 +1746,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     const unsigned long long want = (unsigned long long)opt.subproblems_factor * (unsigned long long)s->num_blocks * (unsigned long long)opt.gpu_world;
     while ((1ull << d) < want && d < 62) ++d;
   }
-  if (d > 62) d = 62;
+  if (d > TB_K_BITS) d = TB_K_BITS;          // the dispenser word keeps its high bits for the epoch
   P.subproblems_power = d;
   P.num_subproblems = 1ull << d;
   *out = s;
@@ -1645,7 +1759,7 @@ extern "C" void tb_destroy(tb_solver* s) {
   for (void* h : s->ipc_opened) cudaIpcCloseMemHandle(h);
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (void* p : s->allocs) cudaFreeAsync(p, (cudaStream_t)0);     // back to the pool, which keeps it
-  if (s->d_bound) cudaFree(s->d_bound);
+  if (s->d_cells) cudaFree(s->d_cells);
   cudaGetLastError();
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -1659,6 +1773,7 @@ static void fill_config(const tb_solver* s, tb_stats* st) {
   st->cluster_size = s->cluster; st->subproblems_power = s->P.subproblems_power; st->blocks_per_sm = s->blocks_per_sm;
   st->shared_bytes = s->shared_bytes; st->store_bytes = s->store_bytes; st->prop_bytes = s->prop_bytes;
   st->eps_num_subproblems = s->P.num_subproblems;
+  st->device_bytes = s->device_bytes;
 }
 
 extern "C" tb_status tb_get_config(tb_solver* s, tb_stats* st) {
@@ -1688,6 +1803,7 @@ static void reduce_stats(const std::vector<BlockStats>& bs, tb_stats* st, int* b
     st->depth_max = std::max(st->depth_max, b.depth_max);
     st->exhaustive = st->exhaustive && b.exhaustive;
     st->eps_solved_subproblems += b.eps_solved; st->eps_skipped_subproblems += b.eps_skipped;
+    st->eps_stolen_subproblems += b.eps_stolen;
     st->num_blocks_done += b.blocks_done;
     st->fixpoint_iterations += b.fixpoint_iterations; st->num_deductions += b.deductions;
     st->bounds_narrowed += b.narrowed;
@@ -1724,7 +1840,7 @@ static unsigned long long host_globaltimer_probe(tb_solver* s);
 __global__ void read_globaltimer_kernel(unsigned long long* out) { *out = globaltimer_ns(); }
 
 static unsigned long long host_globaltimer_probe(tb_solver* s) {
-  unsigned long long* d = (unsigned long long*)s->d_next;   // scratch: overwritten before every launch
+  unsigned long long* d = s->d_cells + TB_CELL_WORDS - 1;    // a spare word of the cell block
   read_globaltimer_kernel<<<1, 1, 0, s->stream>>>(d);
   unsigned long long h = 0;
   cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream);
@@ -1746,12 +1862,14 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   tb_status rc;
   if ((rc = reset_stats(s, s->num_blocks))) return rc;
   P.t_start = host_globaltimer_probe(s);
-  const int pinf = TBD_PINF, zero = 0;
-  const unsigned long long first_free = (unsigned long long)s->num_blocks;
-  // the incumbent cell is only reset when no peer can have written to it yet
-  if (s->peer_cells.empty()) CU(cudaMemcpyAsync(s->d_bound, &pinf, sizeof(int), cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
-  CU(cudaMemcpyAsync(s->d_next, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
+  // A new run = a new epoch (linked solvers make the same sequence of tb_solve calls, so their epochs agree): the
+  // incumbent of the previous run, a late write of a peer that is still in it, a stale stop request are all void
+  // without any reset protocol between the processes. The kernel enters the epoch into the incumbent cell itself.
+  P.epoch = ++s->epoch;
+  const int zero = 0;
+  const unsigned long long first_free = ((unsigned long long)P.epoch << TB_K_BITS) | (unsigned long long)s->num_blocks;
+  CU(cudaMemcpyAsync((int*)(s->d_cells + TB_CELL_STOP) + 1, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_cells + TB_CELL_NEXT, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
   rc = dispatch(s, [&](auto M, auto A) -> tb_status {
     CU(launch_workers(s, solve_kernel<decltype(M)::value, decltype(A)::value>, s->num_blocks, P));
@@ -1769,7 +1887,7 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
     bool must = (stop_flag && *stop_flag) || (s->opt.timeout_ms && now_ms() - t_begin >= (double)s->opt.timeout_ms);
     if (must && !interrupted) {
       interrupted = true;
-      CU(cudaMemcpyAsync(s->d_stop, s->h_pinned_one, sizeof(int), cudaMemcpyHostToDevice, s->copy_stream));
+      CU(cudaMemcpyAsync((int*)(s->d_cells + TB_CELL_STOP) + 1, s->h_pinned_one, sizeof(int), cudaMemcpyHostToDevice, s->copy_stream));
     }
     struct timespec ts = {0, 200000};
     nanosleep(&ts, nullptr);
@@ -1890,12 +2008,10 @@ extern "C" tb_status tb_dive_batch(tb_solver* s, uint64_t first, int32_t count, 
   if ((rc = ensure_batch(s, (size_t)count))) return rc;
   const int grid = std::min(count, s->num_blocks);
   if ((rc = reset_stats(s, grid))) return rc;
-  const int zero = 0, pinf = TBD_PINF;
-  CU(cudaMemcpyAsync(s->d_stop, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
-  if (s->peer_cells.empty()) CU(cudaMemcpyAsync(s->d_bound, &pinf, sizeof(int), cudaMemcpyHostToDevice, s->stream));
   DevParams P = s->P;
   P.cutnodes = 0;
   P.t_start = 0;
+  P.npeers = 0; P.steal = 0; P.observe_stop = 0;     // a dive is a pure function of (root, idx): no incumbent, no stop
   rc = dispatch(s, [&](auto M, auto A) -> tb_status {
     CU(launch_workers(s, dive_kernel<decltype(M)::value, decltype(A)::value>, grid, P,
                       (unsigned long long)first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1));
@@ -1917,17 +2033,16 @@ extern "C" tb_status tb_dive(tb_solver* s, uint64_t idx, int32_t depth, int32_t*
   return tb_dive_batch(s, idx, 1, depth, lb_out, ub_out, remaining_depth, leaf_kind);
 }
 
-// ---- cross-GPU incumbent cells ---------------------------------------------------------------
+// ---- cross-GPU grid cells: incumbent exchange and work stealing ----------------------------------
 static tb_status publish_peers(tb_solver* s) {
-  if (s->peer_cells.empty()) { s->P.peer_bounds = nullptr; s->P.npeers = 0; return TB_OK; }
-  CU(cudaSetDevice(s->device));
-  int** d = nullptr;
-  tb_status rc = dev_alloc(s, &d, s->peer_cells.size());
-  if (rc) return rc;
-  CU(cudaMemcpy(d, s->peer_cells.data(), s->peer_cells.size() * sizeof(int*), cudaMemcpyHostToDevice));
-  s->P.peer_bounds = d; s->P.npeers = (int)s->peer_cells.size();
-  const int pinf = TBD_PINF;
-  CU(cudaMemcpy(s->d_bound, &pinf, sizeof(int), cudaMemcpyHostToDevice));
+  DevParams& P = s->P;
+  P.npeers = 0; P.steal = 0;
+  if (s->peer_cells.empty()) return TB_OK;
+  if (s->peer_cells.size() > TB_MAX_PEERS) { set_error("too many peers"); return TB_ERR_UNSUPPORTED; }
+  for (size_t i = 0; i < s->peer_cells.size(); ++i) { P.peer_cells[i] = s->peer_cells[i]; P.peer_rank[i] = s->peer_ranks[i]; }
+  P.npeers = (int)s->peer_cells.size();
+  // stealing needs every other shard's dispenser (TB_STEAL=0 keeps the static shards)
+  P.steal = (P.npeers == P.world - 1 && env_int("TB_STEAL", 1) != 0) ? 1u : 0u;
   return TB_OK;
 }
 
@@ -1935,7 +2050,7 @@ extern "C" tb_status tb_link_peers(tb_solver** solvers, int32_t n) {
   if (!solvers || n <= 0) { set_error("invalid argument"); return TB_ERR_INVALID; }
   for (int i = 0; i < n; ++i) {
     tb_solver* a = solvers[i];
-    a->peer_cells.clear();
+    a->peer_cells.clear(); a->peer_ranks.clear();
     CU(cudaSetDevice(a->device));
     for (int j = 0; j < n; ++j) {
       if (i == j) continue;
@@ -1948,7 +2063,8 @@ extern "C" tb_status tb_link_peers(tb_solver** solvers, int32_t n) {
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return TB_ERR_CUDA; }
         cudaGetLastError();
       }
-      a->peer_cells.push_back(b->d_bound);
+      a->peer_cells.push_back(b->d_cells);
+      a->peer_ranks.push_back(b->opt.gpu_rank);
     }
   }
   for (int i = 0; i < n; ++i) { tb_status rc = publish_peers(solvers[i]); if (rc) return rc; }
@@ -1960,7 +2076,7 @@ extern "C" tb_status tb_export_bound_handle(tb_solver* s, void* handle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
   CU(cudaSetDevice(s->device));
   cudaIpcMemHandle_t h;
-  CU(cudaIpcGetMemHandle(&h, s->d_bound));
+  CU(cudaIpcGetMemHandle(&h, s->d_cells));
   memcpy(handle64, &h, 64);
   return TB_OK;
 }
@@ -1968,14 +2084,16 @@ extern "C" tb_status tb_export_bound_handle(tb_solver* s, void* handle64) {
 extern "C" tb_status tb_import_peer_bounds(tb_solver* s, const void* handles64, int32_t npeers) {
   if (!s || (npeers && !handles64) || npeers < 0) { set_error("invalid argument"); return TB_ERR_INVALID; }
   CU(cudaSetDevice(s->device));
-  s->peer_cells.clear();
+  s->peer_cells.clear(); s->peer_ranks.clear();
   for (int i = 0; i < npeers; ++i) {
     cudaIpcMemHandle_t h;
     memcpy(&h, (const char*)handles64 + (size_t)i * 64, 64);
     void* p = nullptr;
     CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->ipc_opened.push_back(p);
-    s->peer_cells.push_back((int*)p);
+    s->peer_cells.push_back((unsigned long long*)p);
+    // handles come in rank order with this solver's own rank left out
+    s->peer_ranks.push_back(i < s->opt.gpu_rank ? i : i + 1);
   }
   return publish_peers(s);
 }
@@ -1983,7 +2101,9 @@ extern "C" tb_status tb_import_peer_bounds(tb_solver* s, const void* handles64, 
 extern "C" tb_status tb_read_bound(tb_solver* s, int32_t* bound) {
   if (!s || !bound) { set_error("null argument"); return TB_ERR_INVALID; }
   CU(cudaSetDevice(s->device));
-  CU(cudaMemcpy(bound, s->d_bound, sizeof(int), cudaMemcpyDeviceToHost));
+  unsigned long long w = ~0ull;
+  CU(cudaMemcpy(&w, s->d_cells + TB_CELL_BOUND, sizeof(w), cudaMemcpyDeviceToHost));
+  *bound = (unsigned)(w >> 32) == ~s->epoch ? (int32_t)((unsigned)w ^ 0x80000000u) : TBD_PINF;
   return TB_OK;
 }
 

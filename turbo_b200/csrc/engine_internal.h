@@ -19,11 +19,25 @@ struct DevStrategy {            // StrategyType (barebones :84)
 
 // Per-block statistics: Statistics<> fields written on the device (include/statistics.hpp:137-154).
 struct BlockStats {
-  unsigned long long nodes, fails, solutions, eps_solved, eps_skipped, blocks_done;
+  unsigned long long nodes, fails, solutions, eps_solved, eps_skipped, eps_stolen, blocks_done;
   unsigned long long fixpoint_iterations, deductions, narrowed;
   long long t_fixpoint, t_dive, t_best, t_idle;
   int depth_max, exhaustive, best_bound, has_best, error, pad_;
 };
+
+// Grid cells (unsigned long long words of one GPU's cell block).
+//   TB_CELL_BOUND: GridData::appx_best_bound (:426) as (~epoch << 32) | (bound ^ 0x80000000): an unsigned atomicMin keeps
+//                  the newest epoch and, within it, the smallest bound;
+//   TB_CELL_NEXT : GridData::next_subproblem (:418) as (epoch << 40) | k, counting this GPU's shard idx = k * world + rank;
+//   TB_CELL_STOP : two ints: [0] = epoch in which a peer (or a block of this GPU) asked everybody to stop,
+//                  [1] = raised by the host (UnifiedData::stop, :64) with an async copy.
+#define TB_CELL_BOUND 0
+#define TB_CELL_NEXT 1
+#define TB_CELL_STOP 2
+#define TB_CELL_WORDS 16
+#define TB_MAX_PEERS 31
+#define TB_K_BITS 40
+#define TB_K_MASK ((1ull << TB_K_BITS) - 1ull)
 
 // Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
 // flattened to plain device pointers (no managed memory, no device-side malloc).
@@ -41,6 +55,8 @@ struct DevParams {
   const DevStrategy* strategies;
   unsigned long long num_subproblems, cutnodes, t_start;
   int rank, world, max_depth, npeers;
+  int observe_stop, pad3_;      // 0 for the parity hooks (tb_propagate / tb_dive): the stop cells are neither read nor raised
+  unsigned epoch, steal;        // tb_solve call number of this solver (tags the grid cells); stealing from peers enabled
   int cluster_size, cluster_log2, vc, pad0_;   // STORE_CLUSTER: CTAs per cluster, its log2, variables per CTA slice
   // per-block scratch in global memory, [slot] major
   int* block_root;              // snapshot of the subproblem root (root_store, barebones :89)
@@ -54,11 +70,12 @@ struct DevParams {
   int* snap_tag;                // [slot][nsnap]
   unsigned* snap_flags;         // [slot][nsnap][nwarps * act_fpw / 4]: the chunks' entailment cache at the snapshot (active set)
   int nsnap, pad2_;
-  // grid-shared cells
-  unsigned long long* next_subproblem;   // GridData::next_subproblem (:418), counts this GPU's shard
-  int* appx_best_bound;                  // GridData::appx_best_bound (:426), this GPU's copy
-  int* const* peer_bounds;               // the other GPUs' copies (peer-mapped over NVLink)
-  volatile int* stop;                    // UnifiedData::stop (:64), raised by the host with an async copy
+  // grid-shared cells: one 128-byte block per GPU (TB_CELL_*), the peers' blocks mapped over NVLink.  The incumbent and
+  // the dispenser carry the epoch (the solver's tb_solve call number) in their high bits, so that a write that belongs
+  // to another run of a linked solver can never prune or hand out work in this one (no reset protocol between runs).
+  unsigned long long* cells;             // this GPU's block
+  unsigned long long* peer_cells[TB_MAX_PEERS];   // the other GPUs' blocks (peer-mapped)
+  int peer_rank[TB_MAX_PEERS];           // whose shard a peer's dispenser counts (idx = k * world + peer_rank)
   // active-set fixpoint (TB_FP_*_ACTIVE): slot -> chunks that load it (CSR), and where its flags live in shared memory
   const int* watch_off;                  // vpad + 1 offsets into watch_list
   const int* watch_list;                 // chunk ids, ascending per slot

@@ -223,6 +223,10 @@ void print_config_stats(const Config& c, const tb_stats& st) {       // config.h
   printf("%%%%%%mzn-stat: timeout_ms=%zu\n", c.timeout_ms);
   printf("%%%%%%mzn-stat: threads_per_block=%d\n", st.threads_per_block);
   printf("%%%%%%mzn-stat: stack_size=%zu\n", c.stack_kb * 1000);
+  {
+    tb_device_info di;                                               // config.hpp:258-260
+    if (tb_get_device_info(0, &di) == TB_OK) printf("%%%%%%mzn-stat: cuda_version=%d\n", di.cuda_runtime_version);
+  }
   printf("%%%%%%mzn-stat: cuda_architecture=%d\n", 1000);
   printf("%%%%%%mzn-stat: num_gpus=%d\n", c.gpus);
   printf("%%%%%%mzn-stat: cutnodes=%zu\n", c.stop_after_n_nodes);
@@ -244,6 +248,7 @@ void print_solver_stats(const Stat& S, const tb_stats& st, int verbose, size_t v
   S.u("eps_num_subproblems", st.eps_num_subproblems);
   S.u("eps_solved_subproblems", st.eps_solved_subproblems);
   S.u("eps_skipped_subproblems", st.eps_skipped_subproblems);
+  if (st.eps_stolen_subproblems) S.u("eps_stolen_subproblems", st.eps_stolen_subproblems);
   S.u("num_blocks_done", st.num_blocks_done);
   S.u("fixpoint_iterations", st.fixpoint_iterations);
   S.u("num_deductions", st.num_deductions);
@@ -365,6 +370,10 @@ int main(int argc, char** argv) {
   if (config.gpus > ndev && config.verbose) printf("%% WARNING: -gpus %d is more than the %d visible devices.\n", config.gpus, ndev);
   config.gpus = G;
   std::vector<tb_solver*> solvers((size_t)G, nullptr);
+  if (config.stack_kb) {                                             // -stack (barebones :588-593)
+    for (int g = 0; g < G; ++g)
+      if (tb_set_stack_limit(g, (uint64_t)config.stack_kb * 1000) != TB_OK) { std::cerr << "-stack: " << tb_last_error() << std::endl; return EXIT_FAILURE; }
+  }
   S.i("subproblems_power", config.subproblems_power);
   {
     // one host thread per GPU: context creation, uploads and attribute queries of the G devices overlap
@@ -404,6 +413,18 @@ int main(int argc, char** argv) {
   }
   tb_stats cfg;
   tb_get_config(solvers[0], &cfg);
+  {
+    // barebones :579-581 prints the device heap it raised and the global memory size; here every byte is allocated by
+    // the host before the launch, so heap_memory is what the solvers hold
+    tb_device_info di;
+    uint64_t held = 0;
+    for (int g = 0; g < G; ++g) { tb_stats c; tb_get_config(solvers[(size_t)g], &c); held += c.device_bytes; }
+    if (tb_get_device_info(0, &di) == TB_OK) {
+      S.mem(config.verbose, "heap_memory", held);
+      S.mem(config.verbose, "total_global_mem_bytes", di.total_global_mem_bytes);
+      S.mem(config.verbose, "stack_memory", di.stack_limit_bytes * (uint64_t)cfg.num_blocks * (uint64_t)cfg.threads_per_block);
+    }
+  }
   S.mem(config.verbose, "mem_per_block", cfg.store_bytes * 2 + 320000);
   S.i("num_blocks", (int64_t)cfg.num_blocks * G);
   S.s("memory_configuration", mem_name(cfg.mem_kind));
@@ -421,17 +442,22 @@ int main(int argc, char** argv) {
   std::vector<int32_t> has((size_t)G, 0), exh((size_t)G, 0);
   std::vector<tb_stats> sts((size_t)G);
   std::vector<tb_status> rcs((size_t)G, TB_OK);
+  std::vector<std::string> cerr_solve((size_t)G);
   if (config.verbose) printf("%% GPU kernel started, starting solving...\n");
   const int64_t kernel_start_ns = since_ns();
   if (config.verbose) printf("%% start-up: preprocessing (parse, ternarise, simplify on the GPU) %.3f s, engine creation %.3f s\n", to_sec(init_ns), to_sec(kernel_start_ns - init_ns));
   {
     std::vector<std::thread> th;
     for (int g = 0; g < G; ++g)
-      th.emplace_back([&, g]() { rcs[(size_t)g] = tb_solve(solvers[(size_t)g], &g_stop, blb[(size_t)g].data(), bub[(size_t)g].data(), &has[(size_t)g], &exh[(size_t)g], &sts[(size_t)g]); });
+      th.emplace_back([&, g]() {
+        rcs[(size_t)g] = tb_solve(solvers[(size_t)g], &g_stop, blb[(size_t)g].data(), bub[(size_t)g].data(), &has[(size_t)g], &exh[(size_t)g], &sts[(size_t)g]);
+        if (rcs[(size_t)g] != TB_OK) cerr_solve[(size_t)g] = tb_last_error();      // (the error text is per thread)
+      });
     for (auto& t : th) t.join();
   }
+  int exit_code = 0;
   for (int g = 0; g < G; ++g)
-    if (rcs[(size_t)g] != TB_OK) { std::cerr << "tb_solve failed on GPU " << g << ": " << tb_last_error() << std::endl; }
+    if (rcs[(size_t)g] != TB_OK) { std::cerr << "tb_solve failed on GPU " << g << ": " << cerr_solve[(size_t)g] << std::endl; exit_code = EXIT_FAILURE; }
 
   // ---- reduce over GPUs (reduce_blocks, barebones :1033-1067) ---------------------------------------------------
   int best = -1;
@@ -442,6 +468,7 @@ int main(int argc, char** argv) {
     total.depth_max = std::max(total.depth_max, s.depth_max);
     total.exhaustive = total.exhaustive && s.exhaustive;
     total.eps_solved_subproblems += s.eps_solved_subproblems; total.eps_skipped_subproblems += s.eps_skipped_subproblems;
+    total.eps_stolen_subproblems += s.eps_stolen_subproblems;
     total.num_blocks_done += s.num_blocks_done;
     total.fixpoint_iterations += s.fixpoint_iterations; total.num_deductions += s.num_deductions;
     total.bounds_narrowed += s.bounds_narrowed;
@@ -462,7 +489,6 @@ int main(int argc, char** argv) {
   total.eps_num_subproblems = sts[0].eps_num_subproblems;
   total.threads_per_block = sts[0].threads_per_block;
   if (g_signal || (config.timeout_ms && since_ns() / 1000000 >= (int64_t)config.timeout_ms)) total.exhaustive = 0;
-  int exit_code = 0;
   if (best >= 0) {
     // time-to-optimum includes the time before the kernel started (barebones :501)
     total.timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND] = sts[(size_t)best].timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND] + kernel_start_ns;
