@@ -178,6 +178,19 @@ tb_status tb_import_peer_bounds(tb_solver*, const void* handles64, int32_t npeer
 /* Incumbent of this solver's latest run as its own cell holds it (TB_POS_INF when none). */
 tb_status tb_read_bound(tb_solver*, int32_t* bound);
 
+/* Final gather with one process per GPU ("one gather of {best_bound, best_store, tb_stats} to GPU 0, then
+ * the reduction of reduce_blocks", barebones_dive_and_solve.hpp:1033-1067).  tb_result_pack serialises what the
+ * solver's latest tb_solve returned into tb_result_size() bytes (plain bytes: the caller moves them with whatever
+ * it has - an NCCL/MPI gather, a pipe); tb_result_reduce merges n such buffers laid out `stride` bytes apart:
+ * counters are summed, depths and kernel times take the maximum, the first idle time the minimum, the search was
+ * exhaustive if every shard was, and the best solution is the one with the smallest objective, the earliest found
+ * among equals (for a satisfaction problem: the earliest found).  The driver uses the same pair for its -gpus N
+ * threads. best_lb / best_ub / best_rank may be NULL. */
+size_t tb_result_size(const tb_solver*);
+tb_status tb_result_pack(const tb_solver*, void* buf, size_t cap);
+tb_status tb_result_reduce(const void* bufs, int32_t n, size_t stride, int32_t* best_lb, int32_t* best_ub,
+                           int32_t* has_solution, int32_t* exhaustive, tb_stats* total, int32_t* best_rank);
+
 /* Fills `stats` with the launch configuration chosen by tb_create (num_blocks, mem_kind, ...). */
 tb_status tb_get_config(tb_solver*, tb_stats* stats);
 
@@ -213,6 +226,10 @@ typedef struct {
   char name[64];
 } tb_device_info;
 tb_status tb_get_device_info(int32_t device, tb_device_info* info);
+/* Measured shared-memory read bandwidth of the device (GB/s over all SMs; LDS.64 stream, conflict free) and the
+ * bytes per clock per SM that is at the device's maximum SM clock: the measured denominator of the fixpoint
+ * kernel's roofline (SURVEY.md 8d states the nominal 128 B/clk/SM). bytes_per_clk_per_sm may be NULL. */
+tb_status tb_measure_smem_peak(int32_t device, double* gb_per_s, double* bytes_per_clk_per_sm);
 /* -stack <KB>: per-thread stack limit of the device (cudaLimitStackSize, barebones :588-593). */
 tb_status tb_set_stack_limit(int32_t device, uint64_t bytes);
 

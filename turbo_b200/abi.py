@@ -83,6 +83,15 @@ class TbStats(C.Structure):
         return d
 
 
+class TbResultHeader(C.Structure):
+    """Wire format of tb_result_pack: this header, then lb[nvars], then ub[nvars] (int32)."""
+    _fields_ = [("magic", C.c_uint32), ("nvars", C.c_int32), ("obj_var", C.c_int32), ("has_solution", C.c_int32),
+                ("exhaustive", C.c_int32), ("objective", C.c_int32), ("t_best_ns", C.c_int64), ("stats", TbStats)]
+
+
+RESULT_MAGIC = 0x54425232
+
+
 class TbDeviceInfo(C.Structure):
     _fields_ = [("cuda_runtime_version", C.c_int32), ("cuda_driver_version", C.c_int32), ("sm_count", C.c_int32),
                 ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("pad_", C.c_int32),

@@ -76,8 +76,13 @@ __device__ __forceinline__ void bulk_s2g_issue(void* gdst, const void* ssrc, uns
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_commit_wait_all() {
+// The issuing thread may overwrite the shared source as soon as the copy engine has READ it; the global writes are
+// only waited for (bulk_wait_all) by whoever reads an image back or leaves the kernel.
+__device__ __forceinline__ void bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
@@ -97,11 +102,11 @@ __device__ __forceinline__ void bulk_commit_wait_all() {
 
 struct Ctl {                       // per-CTA control block in static shared memory
   unsigned long long mbar;
-  unsigned long long sel_key;      // arg-min key of the variable selection
+  unsigned long long sel_key[2];   // arg-min key of the variable selection (two cells, used in turn)
   unsigned long long subproblem_k; // counter value of the subproblem being solved: idx = subproblem_k * world + sub_owner
   int sub_owner;                   // the rank whose shard it comes from (this GPU's, or a peer's when it was stolen)
   int flags[3];                    // rotating fixpoint flag words
-  int sel_first;
+  int sel_first[2];
   int stop, leaf, failed;
   int remaining_depth, depth, cur_strategy, next_unassigned, snap_strategy, snap_next_unassigned;
   int best_bound;
@@ -229,6 +234,8 @@ struct Ctx {
   unsigned char* sdyn;     // dynamic shared memory: the store image of this CTA (shared placements)
   const unsigned long long* words;   // the propagator table: global (L2) or shared (TCN_SHARED)
   unsigned mbar_phase;
+  unsigned fp_rot;         // rotation of the three fixpoint flag words, kept across calls (fixpoint3)
+  int sel_par;             // which selection cell the next split() uses
   unsigned narrowed;       // per-thread count of published bounds
   unsigned long long deductions;     // per-warp (lane-uniform) count of propagator evaluations
   int* g_root;             // this block's snapshot (global, same layout as the store)
@@ -332,6 +339,7 @@ struct Ctx {
       const unsigned bytes = (unsigned)(MEM == TB_MEM_STORE_CLUSTER ? P.vc : P.vpad) * 8u;
       const char* src = (const char*)gsrc + (size_t)cta_rank * bytes;
       if (threadIdx.x == 0) {
+        bulk_wait_all();                 // the image may be one this thread wrote a moment ago
         fence_proxy_async();
         mbar_expect_tx(&lc->mbar, bytes);
         for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
@@ -342,8 +350,12 @@ struct Ctx {
       if (MEM == TB_MEM_STORE_CLUSTER) sync();     // every slice has landed before anybody gathers from it
     }
   }
-  __device__ __forceinline__ void save_store(int* gdst) {
-    sync();
+  // `synced`: a worker-wide barrier has passed since the last write to the store (the caller just came out of one).
+  // `settle`: end with a barrier, after which anybody may write to the store again. Without it (single-CTA shared
+  // placements only) the issuing thread 0 alone may, because it has waited for the copy engine to read the image.
+  __device__ __forceinline__ void save_store(int* gdst, const bool synced = false, bool settle = true) {
+    if (MEM == TB_MEM_GLOBAL || MEM == TB_MEM_STORE_CLUSTER) settle = true;
+    if (!synced) sync();
     if (MEM == TB_MEM_GLOBAL) {
       const unsigned bytes = (unsigned)P.vpad * 8u;
       const int4* s4 = (const int4*)(MEM == TB_MEM_GLOBAL ? (const void*)P.block_store + (size_t)slot * 8 * P.vpad : (const void*)sdyn); int4* d4 = (int4*)gdst;
@@ -354,9 +366,9 @@ struct Ctx {
       fence_proxy_async();
       for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
         bulk_s2g_issue(dst + off, (const char*)sdyn + off, min(BULK_CHUNK, bytes - off));
-      bulk_commit_wait_all();
+      bulk_commit_wait_read();
     }
-    sync();
+    if (settle) sync();
   }
 
   // ---- fixpoint (BlockAsynchronousFixpointGPU::fixpoint + warp_fixpoint, barebones :925-965) ---
@@ -512,6 +524,128 @@ struct Ctx {
     sync();
     if (tid < 3) c.flags[tid] = 0;
     sync();
+    return f;
+  }
+
+  // ---- the dense fixpoint, third generation (default; -DTB_FIXPOINT_V2 keeps the loop above) -------------------
+  // Same sweeps, same warp-local WAC1 iteration, same flags; what changed is what a visit that finds nothing to do
+  // (nine out of ten) has to execute:
+  //   * the work path is one cold block: after publishing, ONE re-read of the operands is both the emptiness check
+  //     (failure detection, tbd::emptied) and the snapshot of the next warp-local iteration; failure leaves the
+  //     sweep from there, so the hot loop carries no `dead` / `late change` flags;
+  //   * evaluations are counted as visits (derived from the walk) + re-evaluations (counted in the work path);
+  //   * the fused `ask` stops at the first non-entailed propagator the warp sees in a sweep: the node then cannot
+  //     be a solution, whatever the other chunks say (all-entailed sweeps still check every chunk);
+  //   * every flag the warp reports is warp-uniform: no REDUX before the atomicOr;
+  //   * the three flag words keep rotating across calls, so a fixpoint ends on its last sweep's barrier (the loop
+  //     above spends two more barriers per call on clearing them).
+  struct Walk3 {
+    int ch;                       // current chunk of this warp (uniform)
+    int widx;                     // index of this lane's first word of the chunk the warp visits after the next one
+    Words cur, nxt;               // this lane's words of the current chunk and of the next one (in flight)
+    unsigned extra;               // evaluations beyond one per visit (WAC1 re-evaluations)
+    unsigned pad_evals;           // propagator evaluations spent on padding lanes
+    int changed;                  // some visit published a bound
+    int notent;                   // per lane: non-zero iff some propagator of this lane is not entailed
+  };
+
+  // Returns true when the store failed (the sweep is over for this warp).
+  template <int CLS>
+  __device__ __forceinline__ bool sweep_class3(Hot& h, Walk3& w, const bool wac1, const int nwarps, const int stride) {
+    const StoreRef<MEM>& store = h.store;
+    const int ce = P.cls_begin[CLS + 1];
+    unsigned last_extra = 0;      // re-evaluations of the latest visit that had work, and which chunk that was
+    int last_work_ch = -1;
+    do {
+      int fa[TBC_U], fb[TBC_U], fc[TBC_U];
+      tbd::Snap s[TBC_U];
+      bool work = false;
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) decode_word<CLS>(w.cur.w[u], fa[u], fb[u], fc[u]);
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) work |= tbd::has_work<CLS>(s[u]);
+      if (__any_sync(0xffffffffu, work)) {
+        unsigned n = 0;
+        for (;;) {
+#pragma unroll
+          for (int u = 0; u < TBC_U; ++u) {
+            tbd::Snap nb;
+            tbd::narrow<CLS>(s[u], nb);
+            tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], nb, h.narrowed);
+          }
+          publish_fence();
+          bool empty = false;
+          work = false;
+#pragma unroll
+          for (int u = 0; u < TBC_U; ++u) {
+            tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
+            empty |= tbd::snapshot_empty<CLS>(s[u]);
+          }
+          ++n;
+          if (__any_sync(0xffffffffu, empty)) { w.changed = 1; w.extra += wac1 ? n : 0u; return true; }
+          if (!wac1) break;
+#pragma unroll
+          for (int u = 0; u < TBC_U; ++u) work |= tbd::has_work<CLS>(s[u]);
+          if (!__any_sync(0xffffffffu, work)) break;
+        }
+        w.changed = 1;
+        last_extra = wac1 ? n : 0u; last_work_ch = w.ch;
+        w.extra += last_extra;
+      }
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) w.notent |= tbd::not_entailed_bits<CLS>(s[u]);
+      w.ch += nwarps;
+      w.cur = w.nxt;
+      w.nxt = load_words(h.words, w.widx);
+      w.widx += stride;
+    } while (w.ch < ce);
+    // the class's last chunk is padded with copies of its last propagator: do not count those lanes
+    if (w.ch - nwarps == ce - 1) w.pad_evals += (1u + (last_work_ch == ce - 1 ? last_extra : 0u)) * (unsigned)(32 * TBC_U - P.cls_last[CLS]);
+    return false;
+  }
+
+  __device__ __forceinline__ int fixpoint3(int& iters) {
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = T >> 5;
+    const int stride = nwarps * 32 * TBC_U;
+    const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
+    Hot h;
+    h.store = store; h.words = words; h.narrowed = narrowed;
+    unsigned long long ded = 0;
+    unsigned rot = fp_rot;
+    int it = 0, f;
+    for (;; ++it) {
+      Walk3 w;
+      w.ch = warp; w.extra = w.pad_evals = 0; w.changed = 0; w.notent = 0;
+      w.widx = (warp * 32 + lane) * TBC_U;
+      w.cur = load_words(h.words, w.widx);
+      w.widx += stride;
+      w.nxt = load_words(h.words, w.widx);
+      w.widx += stride;
+      bool failed = false;
+#define TB_SWEEP(CLS) if (!failed && w.ch < P.cls_begin[CLS + 1]) failed = sweep_class3<CLS>(h, w, wac1, nwarps, stride);
+      TB_SWEEP(TBC_ADD_S) TB_SWEEP(TBC_ADD_XK) TB_SWEEP(TBC_ADD_ZK) TB_SWEEP(TBC_ADD_G)
+      TB_SWEEP(TBC_MUL) TB_SWEEP(TBC_TDIV) TB_SWEEP(TBC_TMOD) TB_SWEEP(TBC_MIN) TB_SWEEP(TBC_MAX)
+      TB_SWEEP(TBC_EQ_S) TB_SWEEP(TBC_EQ_T) TB_SWEEP(TBC_EQ_F) TB_SWEEP(TBC_EQ_ZK) TB_SWEEP(TBC_EQ_G)
+      TB_SWEEP(TBC_LEQ_S) TB_SWEEP(TBC_LEQ_T) TB_SWEEP(TBC_LEQ_F) TB_SWEEP(TBC_LEQ_ZK) TB_SWEEP(TBC_LEQ_G)
+#undef TB_SWEEP
+      // one evaluation per completed visit, one more for the visit a failure interrupted, plus the re-evaluations
+      const unsigned visits = (unsigned)(w.ch - warp) / (unsigned)nwarps + (failed ? 1u : 0u);
+      ded += (unsigned long long)(visits + w.extra) * (unsigned long long)(32 * TBC_U) - (unsigned long long)w.pad_evals;
+      const int bits = (w.changed ? F_CHANGED : 0) | (failed ? F_FAILED : 0) | (__any_sync(0xffffffffu, w.notent != 0) ? F_NOT_ENTAILED : 0);
+      const unsigned slot = rot % 3u;
+      if (lane == 0 && bits) atomicOr(&c.flags[slot], bits);
+      if (tid == 0) c.flags[(rot + 1u) % 3u] = 0;
+      sync();
+      f = c.flags[slot];
+      ++rot;
+      if (!(f & F_CHANGED) || (f & F_FAILED)) break;
+    }
+    fp_rot = rot;
+    iters = it + 1;
+    narrowed = h.narrowed;
+    deductions += ded;
     return f;
   }
 
@@ -672,6 +806,14 @@ struct Ctx {
     return f;
   }
 
+  __device__ __forceinline__ int dense_fixpoint(int& iters) {
+#if defined(TB_FIXPOINT_V2)
+    return fixpoint(iters);
+#else
+    return fixpoint3(iters);
+#endif
+  }
+
   // ---- propagate() (barebones :903-1031) -----------------------------------------------------------
   // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
   // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
@@ -682,7 +824,7 @@ struct Ctx {
     bool pre_failed = P.root_failed != 0;       // a referenced variable is already empty in the root store
     if (P.obj_var >= 0) { int l, u; store.ld(P.obj_var, l, u); pre_failed |= l > u; }
     if (pre_failed) f = F_FAILED;
-    else f = ACT ? fixpoint_active(iters) : fixpoint(iters);
+    else f = ACT ? fixpoint_active(iters) : dense_fixpoint(iters);
     const bool failed = (f & F_FAILED) != 0;
     const bool solution = !failed && !(f & F_NOT_ENTAILED);
     unsigned long long t1 = 0;
@@ -790,20 +932,22 @@ struct Ctx {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
         if (other < key) key = other;
       }
-      if (lane == 0 && key != ~0ull) { atomicMin(&c.sel_key, key); atomicMin(&c.sel_first, first); }
+      // two selection cells used in turn: thread 0 re-arms the other one while everybody reads this one
+      const int par = sel_par;
+      sel_par ^= 1;
+      if (lane == 0 && key != ~0ull) { atomicMin(&c.sel_key[par], key); atomicMin(&c.sel_first[par], first); }
       sync();
-      const unsigned long long best = c.sel_key;
-      sync();
+      const unsigned long long best = c.sel_key[par];
       if (tid == 0) {
         if (best != ~0ull) {
-          c.next_unassigned = c.sel_first;
+          c.next_unassigned = c.sel_first[par];
           int i = (int)(unsigned)(best & 0xffffffffu);
           push_decision(strat.val_order, in_store ? i : strat.vars[i]);
         } else {
           c.cur_strategy = s + 1;
           c.next_unassigned = 0;
         }
-        c.sel_key = ~0ull; c.sel_first = INT32_MAX;
+        c.sel_key[par ^ 1] = ~0ull; c.sel_first[par ^ 1] = INT32_MAX;
       }
       sync();
       if (best != ~0ull) return c.pushed != 0;
@@ -960,7 +1104,8 @@ struct Ctx {
             // copying instead of recomputation: keep this node's fixpoint, so that the right branch of the decision
             // restarts from here (one changed variable) instead of from the subproblem root plus a replay
             const int j = c.depth - 1;
-            save_store(g_snap + (size_t)(j % P.nsnap) * 2 * P.vpad);
+            // (split() ended on a barrier; the decision below is applied by the thread that waited for the copy engine)
+            save_store(g_snap + (size_t)(j % P.nsnap) * 2 * P.vpad, true, false);
             if (tid == 0) g_snap_tag[j % P.nsnap] = j;
             if (ACT) {
               // the fixpoint has just converged: no moved bit, no dirty chunk; keep the entailment cache with the image
@@ -1058,6 +1203,8 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   k.sdyn = dyn;
   k.words = P.words;
   k.mbar_phase = 0;
+  k.fp_rot = 0;
+  k.sel_par = 0;
   k.narrowed = 0;
   k.deductions = 0;
   k.g_root = P.block_root + (size_t)slot * 2 * P.vpad;
@@ -1070,7 +1217,7 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   if (threadIdx.x == 0) {
     mbar_init(&local->mbar, 1);
     local->flags[0] = local->flags[1] = local->flags[2] = 0;
-    local->sel_key = ~0ull; local->sel_first = INT32_MAX;
+    local->sel_key[0] = local->sel_key[1] = ~0ull; local->sel_first[0] = local->sel_first[1] = INT32_MAX;
     local->stop = 0; local->leaf = 0; local->failed = 0; local->depth = 0; local->pushed = 0;
     local->cur_strategy = 0; local->next_unassigned = 0; local->snap_strategy = 0; local->snap_next_unassigned = 0;
     local->best_bound = TBD_PINF; local->remaining_depth = 0;
@@ -1108,6 +1255,7 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
     atomicAdd(&k.st->narrowed, (unsigned long long)n);
     if (k.deductions) atomicAdd(&k.st->deductions, k.deductions);
   }
+  if (threadIdx.x == 0) bulk_wait_all();     // images still on their way to global memory (best store, snapshots)
   k.sync();        // with a cluster: nobody leaves while a peer may still touch its shared memory
 }
 
@@ -1170,7 +1318,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_
       if (empty_seen) atomicOr(&c.leaf, 1);
       k.sync();
       if (c.leaf) { f = F_FAILED; iters = 0; k.sync(); }
-      else f = ACT ? k.fixpoint_active(iters) : k.fixpoint(iters);
+      else f = ACT ? k.fixpoint_active(iters) : k.dense_fixpoint(iters);
       if (tid == 0) {
         k.st->fixpoint_iterations += (unsigned long long)iters;
         k.st->nodes++;
@@ -1275,7 +1423,7 @@ struct tb_solver {
   DevParams P;
   tb_options opt;
   int device = 0;
-  int nvars = 0, nprops = 0;
+  int nvars = 0, nprops = 0, root_obj_var = -1;
   int mem_kind = TB_MEM_GLOBAL, threads = 256, num_blocks = 1, blocks_per_sm = 1, cluster = 1;
   TnfLayout layout;                   // device table + variable placement (layout.h)
   std::vector<int32_t> root_lb, root_ub;   // the root domains (precondition check of tb_propagate)
@@ -1291,6 +1439,10 @@ struct tb_solver {
   std::vector<void*> ipc_opened;
   unsigned long long* d_cells = nullptr;   // this GPU's cell block: incumbent, dispenser, stop
   unsigned epoch = 0;                 // number of tb_solve calls so far: tags the cells of the current run
+  // what the latest tb_solve returned (tb_result_pack)
+  tb_stats last_stats;
+  int last_has = 0, last_exhaustive = 0, last_valid = 0;
+  std::vector<int32_t> last_lb, last_ub;
   int scratch_blocks = 0;             // number of per-block scratch slots allocated
   // batch buffers (grown on demand)
   int *d_in_lb = nullptr, *d_in_ub = nullptr, *d_out_lb = nullptr, *d_out_ub = nullptr, *d_out_i0 = nullptr, *d_out_i1 = nullptr;
@@ -1343,6 +1495,9 @@ template <class F>
 static tb_status dispatch(const tb_solver* s, F&& f) {
   using Dense = std::false_type;
   using Active = std::true_type;          // active-set fixpoint: shared-memory placements only
+#ifdef TB_SASS_PROBE      // (developer builds: one instantiation, to read its SASS quickly)
+  return f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{});
+#else
   switch (s->mem_kind) {
     case TB_MEM_GLOBAL: return f(std::integral_constant<int, TB_MEM_GLOBAL>{}, Dense{});
     case TB_MEM_STORE_SHARED:
@@ -1354,6 +1509,7 @@ static tb_status dispatch(const tb_solver* s, F&& f) {
   }
   set_error("unsupported memory kind");
   return TB_ERR_UNSUPPORTED;
+#endif
 }
 
 // Launch `workers` workers: one CTA each, or one cluster of s->cluster CTAs each (STORE_CLUSTER).
@@ -1605,6 +1761,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   s->nvars = pb->nvars; s->nprops = pb->nprops;
   P.nvars = pb->nvars; P.nprops = pb->nprops;
   P.obj_var = pb->obj_var;
+  s->root_obj_var = pb->obj_var;
   P.has_eps_strategy = pb->has_eps_strategy;
   P.fixpoint_kind = (opt.fixpoint == TB_FP_AC1 || opt.fixpoint == TB_FP_AC1_ACTIVE) ? TB_FP_AC1 : TB_FP_WAC1;
   s->want_active = opt.fixpoint == TB_FP_AC1_ACTIVE || opt.fixpoint == TB_FP_WAC1_ACTIVE;
@@ -1737,6 +1894,29 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
       cudaEventCreate(&s->ev_start) != cudaSuccess || cudaEventCreate(&s->ev_stop) != cudaSuccess ||
       (s->h_pinned_one = pinned_one()) == nullptr) {
     set_error("stream/event creation failed"); return fail(TB_ERR_CUDA);
+  }
+
+  // The propagator table is what every block streams from L2 in every sweep, next to the snapshot images that flow
+  // through L2 once: ask for the table's lines to persist (access policy window on the solver's stream; TB_L2_PERSIST=0
+  // turns it off). Best effort: a device without the feature just keeps its normal policy.
+  if (env_int("TB_L2_PERSIST", 1) != 0 && s->mem_kind != TB_MEM_TCN_SHARED && s->layout.words.size()) {
+    cudaDeviceProp dp;
+    if (cudaGetDeviceProperties(&dp, s->device) == cudaSuccess && dp.persistingL2CacheMaxSize > 0 && dp.accessPolicyMaxWindowSize > 0) {
+      const size_t bytes = std::min<size_t>(s->layout.words.size() * 8, (size_t)dp.accessPolicyMaxWindowSize);
+      size_t cur = 0;
+      cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+      const size_t want = std::min<size_t>((size_t)dp.persistingL2CacheMaxSize, std::max<size_t>(bytes * 2, 4u << 20));
+      if (cur < want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.base_ptr = (void*)P.words;
+      av.accessPolicyWindow.num_bytes = bytes;
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+      cudaGetLastError();
+    }
   }
 
   // II. number of subproblems (barebones :548-555), generalised to the GPU count
@@ -1907,14 +2087,103 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   st.kernel_ms = kms;
   st.timers_ns[TB_TIMER_OVERALL] = (int64_t)((now_ms() - t_begin) * 1e6);
   if (has_solution) *has_solution = best_block >= 0;
-  if (best_block >= 0 && best_lb && best_ub) {
+  s->last_lb.assign((size_t)std::max(1, s->nvars), 0); s->last_ub.assign((size_t)std::max(1, s->nvars), 0);
+  if (best_block >= 0) {
     std::vector<int> img((size_t)2 * P.vpad);
     CU(cudaMemcpy(img.data(), P.block_best + (size_t)best_block * 2 * P.vpad, img.size() * sizeof(int), cudaMemcpyDeviceToHost));
-    unpack_store(s, img.data(), best_lb, best_ub);
+    unpack_store(s, img.data(), s->last_lb.data(), s->last_ub.data());
+    if (best_lb && best_ub && s->nvars) { memcpy(best_lb, s->last_lb.data(), (size_t)s->nvars * 4); memcpy(best_ub, s->last_ub.data(), (size_t)s->nvars * 4); }
   }
   if (exhaustive) *exhaustive = st.exhaustive;
   if (stats) *stats = st;
+  s->last_stats = st; s->last_has = best_block >= 0; s->last_exhaustive = st.exhaustive; s->last_valid = 1;
   return rc;
+}
+
+// ---- final gather across processes (reduce_blocks, barebones :1033-1067, across GPUs) -------------------
+struct ResultHeader {
+  uint32_t magic; int32_t nvars, obj_var, has_solution, exhaustive, objective;
+  int64_t t_best_ns;
+  tb_stats stats;
+};
+static const uint32_t kResultMagic = 0x54425232u;   // "TBR2"
+
+extern "C" size_t tb_result_size(const tb_solver* s) {
+  return s ? sizeof(ResultHeader) + (size_t)2 * (size_t)s->nvars * sizeof(int32_t) : 0;
+}
+
+extern "C" tb_status tb_result_pack(const tb_solver* s, void* buf, size_t cap) {
+  if (!s || !buf) { set_error("null argument"); return TB_ERR_INVALID; }
+  if (!s->last_valid) { set_error("tb_result_pack: no tb_solve has completed on this solver"); return TB_ERR_INVALID; }
+  if (cap < tb_result_size(s)) { set_error("tb_result_pack: buffer too small"); return TB_ERR_INVALID; }
+  ResultHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = kResultMagic; h.nvars = s->nvars; h.obj_var = s->root_obj_var; h.has_solution = s->last_has; h.exhaustive = s->last_exhaustive;
+  h.objective = (s->last_has && s->root_obj_var >= 0) ? s->last_lb[(size_t)s->root_obj_var] : TBD_PINF;
+  h.t_best_ns = s->last_stats.timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND];
+  h.stats = s->last_stats;
+  char* p = (char*)buf;
+  memcpy(p, &h, sizeof(h));
+  if (s->nvars) {
+    memcpy(p + sizeof(h), s->last_lb.data(), (size_t)s->nvars * 4);
+    memcpy(p + sizeof(h) + (size_t)s->nvars * 4, s->last_ub.data(), (size_t)s->nvars * 4);
+  }
+  return TB_OK;
+}
+
+extern "C" tb_status tb_result_reduce(const void* bufs, int32_t n, size_t stride, int32_t* best_lb, int32_t* best_ub,
+                                      int32_t* has_solution, int32_t* exhaustive, tb_stats* total, int32_t* best_rank) {
+  if (!bufs || n <= 0 || stride < sizeof(ResultHeader)) { set_error("tb_result_reduce: invalid argument"); return TB_ERR_INVALID; }
+  tb_stats t;
+  memset(&t, 0, sizeof(t));
+  t.exhaustive = 1;
+  int best = -1;
+  ResultHeader hb;
+  memset(&hb, 0, sizeof(hb));
+  for (int r = 0; r < n; ++r) {
+    ResultHeader h;
+    memcpy(&h, (const char*)bufs + (size_t)r * stride, sizeof(h));
+    if (h.magic != kResultMagic || (r && h.nvars != hb.nvars && best >= 0)) { set_error("tb_result_reduce: malformed buffer"); return TB_ERR_INVALID; }
+    if (stride < sizeof(ResultHeader) + (size_t)2 * (size_t)h.nvars * 4) { set_error("tb_result_reduce: stride smaller than a result"); return TB_ERR_INVALID; }
+    const tb_stats& s = h.stats;
+    if (r == 0) {                      // the launch configuration is the same on every GPU
+      t.threads_per_block = s.threads_per_block; t.mem_kind = s.mem_kind; t.cluster_size = s.cluster_size;
+      t.subproblems_power = s.subproblems_power; t.blocks_per_sm = s.blocks_per_sm; t.eps_num_subproblems = s.eps_num_subproblems;
+      t.shared_bytes = s.shared_bytes; t.store_bytes = s.store_bytes; t.prop_bytes = s.prop_bytes;
+      t.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE] = s.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE];
+    }
+    t.num_blocks += s.num_blocks;
+    t.nodes += s.nodes; t.fails += s.fails; t.solutions += s.solutions;
+    t.depth_max = std::max(t.depth_max, s.depth_max);
+    t.exhaustive = t.exhaustive && s.exhaustive && h.exhaustive;
+    t.eps_solved_subproblems += s.eps_solved_subproblems; t.eps_skipped_subproblems += s.eps_skipped_subproblems;
+    t.eps_stolen_subproblems += s.eps_stolen_subproblems;
+    t.num_blocks_done += s.num_blocks_done;
+    t.fixpoint_iterations += s.fixpoint_iterations; t.num_deductions += s.num_deductions; t.bounds_narrowed += s.bounds_narrowed;
+    t.cumulative_time_block_ns += s.cumulative_time_block_ns;
+    t.device_bytes += s.device_bytes;
+    for (int k = 0; k < TB_NUM_TIMERS; ++k)
+      if (k != TB_TIMER_LATEST_BEST_OBJ_FOUND && k != TB_TIMER_FIRST_BLOCK_IDLE && k != TB_TIMER_OVERALL) t.timers_ns[k] += s.timers_ns[k];
+    t.timers_ns[TB_TIMER_OVERALL] = std::max(t.timers_ns[TB_TIMER_OVERALL], s.timers_ns[TB_TIMER_OVERALL]);
+    t.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE] = std::min(t.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE], s.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE]);
+    t.kernel_ms = std::max(t.kernel_ms, s.kernel_ms);
+    if (h.has_solution) {
+      const bool better = best < 0 || (h.obj_var >= 0 ? (h.objective < hb.objective || (h.objective == hb.objective && h.t_best_ns <= hb.t_best_ns))
+                                                      : h.t_best_ns < hb.t_best_ns);
+      if (better) { best = r; hb = h; }
+    } else if (best < 0) hb.nvars = h.nvars;
+  }
+  if (best >= 0) {
+    t.timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND] = hb.t_best_ns;
+    const char* p = (const char*)bufs + (size_t)best * stride + sizeof(ResultHeader);
+    if (best_lb && hb.nvars) memcpy(best_lb, p, (size_t)hb.nvars * 4);
+    if (best_ub && hb.nvars) memcpy(best_ub, p + (size_t)hb.nvars * 4, (size_t)hb.nvars * 4);
+  }
+  if (has_solution) *has_solution = best >= 0;
+  if (exhaustive) *exhaustive = t.exhaustive;
+  if (total) *total = t;
+  if (best_rank) *best_rank = best;
+  return TB_OK;
 }
 
 static tb_status ensure_batch(tb_solver* s, size_t n) {

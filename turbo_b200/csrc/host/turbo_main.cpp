@@ -459,32 +459,16 @@ int main(int argc, char** argv) {
   for (int g = 0; g < G; ++g)
     if (rcs[(size_t)g] != TB_OK) { std::cerr << "tb_solve failed on GPU " << g << ": " << cerr_solve[(size_t)g] << std::endl; exit_code = EXIT_FAILURE; }
 
-  // ---- reduce over GPUs (reduce_blocks, barebones :1033-1067) ---------------------------------------------------
+  // ---- reduce over GPUs (reduce_blocks, barebones :1033-1067): the same pack / reduce pair a one-process-per-GPU
+  // launcher gathers with (tb_result_pack + NCCL gather + tb_result_reduce) ------------------------------------------
   int best = -1;
-  for (int g = 0; g < G; ++g) {
-    const tb_stats& s = sts[(size_t)g];
-    total.num_blocks += s.num_blocks;
-    total.nodes += s.nodes; total.fails += s.fails; total.solutions += s.solutions;
-    total.depth_max = std::max(total.depth_max, s.depth_max);
-    total.exhaustive = total.exhaustive && s.exhaustive;
-    total.eps_solved_subproblems += s.eps_solved_subproblems; total.eps_skipped_subproblems += s.eps_skipped_subproblems;
-    total.eps_stolen_subproblems += s.eps_stolen_subproblems;
-    total.num_blocks_done += s.num_blocks_done;
-    total.fixpoint_iterations += s.fixpoint_iterations; total.num_deductions += s.num_deductions;
-    total.bounds_narrowed += s.bounds_narrowed;
-    total.cumulative_time_block_ns += s.cumulative_time_block_ns;
-    for (int t = 0; t < TB_NUM_TIMERS; ++t)
-      if (t != TB_TIMER_LATEST_BEST_OBJ_FOUND && t != TB_TIMER_FIRST_BLOCK_IDLE && t != TB_TIMER_OVERALL) total.timers_ns[t] += s.timers_ns[t];
-    total.kernel_ms = std::max(total.kernel_ms, s.kernel_ms);
-    int64_t idle = s.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE];
-    if (g == 0 || idle < total.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE]) total.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE] = idle;
-    if (has[(size_t)g]) {
-      if (best < 0) best = g;
-      else if (pb->obj_var >= 0) {
-        int32_t a = blb[(size_t)g][(size_t)pb->obj_var], b = blb[(size_t)best][(size_t)pb->obj_var];
-        if (a < b || (a == b && s.timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND] <= sts[(size_t)best].timers_ns[TB_TIMER_LATEST_BEST_OBJ_FOUND])) best = g;
-      }
-    }
+  {
+    const size_t rsz = tb_result_size(solvers[0]);
+    std::vector<char> packed(rsz * (size_t)G);
+    for (int g = 0; g < G; ++g)
+      if (tb_result_pack(solvers[(size_t)g], packed.data() + rsz * (size_t)g, rsz) != TB_OK) { std::cerr << "tb_result_pack: " << tb_last_error() << std::endl; return EXIT_FAILURE; }
+    int32_t any = 0, exh_all = 0;
+    if (tb_result_reduce(packed.data(), G, rsz, nullptr, nullptr, &any, &exh_all, &total, &best) != TB_OK) { std::cerr << "tb_result_reduce: " << tb_last_error() << std::endl; return EXIT_FAILURE; }
   }
   total.eps_num_subproblems = sts[0].eps_num_subproblems;
   total.threads_per_block = sts[0].threads_per_block;

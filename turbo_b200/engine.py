@@ -100,6 +100,47 @@ def device_count():
     return int(lib().tb_device_count())
 
 
+def result_reduce(buffers):
+    """tb_result_reduce over a list of packed results (bytes / uint8 arrays of equal length), rank order."""
+    L = lib()
+    L.tb_result_reduce.argtypes = [C.c_void_p, C.c_int32, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(abi.TbStats), C.POINTER(C.c_int32)]
+    L.tb_result_reduce.restype = C.c_int
+    bufs = [np.frombuffer(bytes(b), dtype=np.uint8) for b in buffers]
+    stride = len(bufs[0])
+    flat = np.ascontiguousarray(np.concatenate(bufs))
+    hdr = abi.TbResultHeader.from_buffer_copy(flat[:C.sizeof(abi.TbResultHeader)].tobytes())
+    nv = max(1, hdr.nvars)
+    lb, ub = np.zeros(nv, np.int32), np.zeros(nv, np.int32)
+    has, exh, best = C.c_int32(0), C.c_int32(0), C.c_int32(-1)
+    st = abi.TbStats()
+    _check(L.tb_result_reduce(flat.ctypes.data_as(C.c_void_p), len(bufs), stride, _p(lb), _p(ub), C.byref(has), C.byref(exh),
+                              C.byref(st), C.byref(best)))
+    return dict(lb=lb[:hdr.nvars], ub=ub[:hdr.nvars], has_solution=bool(has.value), exhaustive=bool(exh.value),
+                stats=st.as_dict(), best_rank=best.value)
+
+
+def device_info(device=0):
+    L = lib()
+    L.tb_get_device_info.argtypes = [C.c_int32, C.POINTER(abi.TbDeviceInfo)]
+    L.tb_get_device_info.restype = C.c_int
+    info = abi.TbDeviceInfo()
+    _check(L.tb_get_device_info(device, C.byref(info)))
+    d = {n: getattr(info, n) for n, _ in info._fields_ if n not in ("pad_", "name")}
+    d["name"] = info.name.decode()
+    return d
+
+
+def measure_smem_peak(device=0):
+    """Measured shared-memory read bandwidth (GB/s over all SMs) and bytes/clk/SM at the maximum SM clock."""
+    L = lib()
+    L.tb_measure_smem_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tb_measure_smem_peak.restype = C.c_int
+    gbs, bpc = C.c_double(0), C.c_double(0)
+    _check(L.tb_measure_smem_peak(device, C.byref(gbs), C.byref(bpc)))
+    return dict(gb_per_s=gbs.value, bytes_per_clk_per_sm=bpc.value)
+
+
 class Solver:
     """One engine instance bound to one CUDA device (tb_solver)."""
 
@@ -198,6 +239,18 @@ class Solver:
         blob = b"".join(handles)
         buf = C.create_string_buffer(blob, len(blob))
         _check(lib().tb_import_peer_bounds(self._h, C.cast(buf, C.c_void_p), len(handles)))
+
+    def result_pack(self):
+        """The latest solve() of this solver as bytes (tb_result_pack): what one rank contributes to the final gather."""
+        L = lib()
+        L.tb_result_size.argtypes = [C.c_void_p]
+        L.tb_result_size.restype = C.c_size_t
+        L.tb_result_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.tb_result_pack.restype = C.c_int
+        n = L.tb_result_size(self._h)
+        buf = np.zeros(n, np.uint8)
+        _check(L.tb_result_pack(self._h, buf.ctypes.data_as(C.c_void_p), n))
+        return buf
 
     def read_bound(self):
         v = C.c_int32(0)
