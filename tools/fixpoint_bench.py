@@ -42,12 +42,13 @@ def measure(pb, repeat=20, fp="wac1", mem="auto", tpb=0, blocks=0, device=0, rou
     ded = best["num_deductions"]
     smem_bytes = 24.0 * ded + 4.0 * best["bounds_narrowed"]
     clk = sm_mhz or 1965.0
-    peak = 128 * 148 * clk * 1e6 / 1e9
+    sms = engine.device_info(device)["sm_count"]
+    peak = 128 * sms * clk * 1e6 / 1e9
     return {"workload_vars": pb.nvars, "workload_props": pb.nprops, "fixpoint": fp, "memory_configuration": abi.MEM_NAMES.get(cfg["mem_kind"]),
             "blocks": nb, "threads_per_block": cfg["threads_per_block"], "repeat": repeat, "kernel_ms": best["kernel_ms"],
             "propagations": ded, "sweeps": best["fixpoint_iterations"], "bounds_narrowed": best["bounds_narrowed"],
             "propagations_per_sec": ded / secs, "smem_gbs": smem_bytes / secs / 1e9, "smem_peak_gbs": peak,
-            "smem_frac": smem_bytes / secs / 1e9 / peak, "props_per_clk_per_sm": ded / secs / (clk * 1e6) / 148}
+            "smem_frac": smem_bytes / secs / 1e9 / peak, "props_per_clk_per_sm": ded / secs / (clk * 1e6) / sms}
 
 
 def main():

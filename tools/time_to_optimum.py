@@ -24,10 +24,11 @@ def main():
     ap.add_argument("--timeout-ms", type=int, default=20000)
     ap.add_argument("--fp", default="wac1")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--sub", type=int, default=-1, help="EPS depth (-1 = auto)")
     a = ap.parse_args()
     pb, info = (golden_io.load_simplified_problem(a.workload.split(':', 1)[1]) if a.workload.startswith('simplified:')
                 else golden_io.load(a.workload))
-    with engine.Solver(pb, device=a.device, timeout_ms=a.timeout_ms,
+    with engine.Solver(pb, device=a.device, timeout_ms=a.timeout_ms, subproblems_power=a.sub,
                        fixpoint=abi.FP_KINDS[a.fp]) as s:
         cfg = s.config()
         r = s.solve()
