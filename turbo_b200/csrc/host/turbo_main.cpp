@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -29,7 +30,7 @@ struct Config {                      // Configuration<> (include/config.hpp:32-5
   int verbose = 0;
   size_t timeout_ms = 0, or_nodes = 0, subproblems_factor = 300, stack_kb = 0, wac1_threshold = 0, seed = 0;
   int subproblems_power = -1;
-  std::string arch = "barebones", fixpoint = "wac1", eps_var_order = "default", eps_value_order = "default";
+  std::string arch = "barebones", fixpoint = "auto", eps_var_order = "default", eps_value_order = "default";
   std::string problem_path, version, hardware;
   int gpus = 1;                      // extension: number of B200s to shard the subproblems over
   int threads_per_block = 0;         // extension: 0 = placement policy decides
@@ -48,7 +49,7 @@ void usage_and_exit(const std::string& prog) {
   std::cout << "\t-v: Print log messages; repeat for more." << std::endl;
   std::cout << "\t-p 48 / -or 48: number of thread blocks searching in parallel (0 = automatic)." << std::endl;
   std::cout << "\t-arch: barebones is the only GPU architecture; gpu and hybrid are mapped onto it. cpu is not available in this build." << std::endl;
-  std::cout << "\t-fp <ac1|wac1|ac1_active|wac1_active>: fixpoint strategy (default wac1); the _active kinds only re-evaluate propagators whose variables changed." << std::endl;
+  std::cout << "\t-fp <ac1|wac1|ac1_active|wac1_active>: fixpoint strategy (default: wac1_active where it pays, i.e. on tables of 128 chunks and more in shared memory, wac1 elsewhere); the _active kinds only re-evaluate propagators whose variables changed: same fixpoints, same search." << std::endl;
   std::cout << "\t-sub 12: create 2^12 subproblems (-1: at least subfactor * blocks * gpus)." << std::endl;
   std::cout << "\t-cutnodes 1000: stop a block after 1000 nodes (0 for no limit)." << std::endl;
   std::cout << "\t-globalmem: keep the variable store in global memory." << std::endl;
@@ -145,7 +146,7 @@ void print_commandline(const Config& c, const char* prog) {      // config.hpp:1
   if (c.disable_simplify) printf("-disable_simplify ");
   if (c.force_ternarize) printf("-force_ternarize ");
   if (c.disable_network_analysis) printf("-disable_network_analysis ");
-  printf("-fp %s ", c.fixpoint.c_str());
+  if (c.fixpoint != "auto") printf("-fp %s ", c.fixpoint.c_str());
   if (c.fixpoint == "wac1" || c.fixpoint == "wac1_active") printf("-wac1_threshold %zu ", c.wac1_threshold);
   printf("-seed %zu -eps_var_order %s -eps_value_order %s ", c.seed, c.eps_var_order.c_str(), c.eps_value_order.c_str());
   if (!c.version.empty()) printf("-version %s ", c.version.c_str());
@@ -212,9 +213,10 @@ void print_config_stats(const Config& c, const tb_stats& st) {       // config.h
   printf("%%%%%%mzn-stat: version=\"%s\"\n", c.version.empty() ? "1.3.0-b200" : c.version.c_str());
   printf("%%%%%%mzn-stat: hardware=\"%s\"\n", c.hardware.empty() ? "unspecified" : c.hardware.c_str());
   printf("%%%%%%mzn-stat: arch=\"%s\"\n", "barebones");
-  printf("%%%%%%mzn-stat: fixpoint=\"%s\"\n", c.fixpoint.c_str());
+  static const char* kFp[] = {"ac1", "wac1", "ac1_active", "wac1_active"};
+  printf("%%%%%%mzn-stat: fixpoint=\"%s\"\n", kFp[st.fixpoint_in_effect & 3]);
   printf("%%%%%%mzn-stat: subproblems_factor=%zu\n", c.subproblems_factor);
-  if (c.fixpoint == "wac1" || c.fixpoint == "wac1_active") printf("%%%%%%mzn-stat: wac1_threshold=%zu\n", c.wac1_threshold);
+  if (st.fixpoint_in_effect & 1) printf("%%%%%%mzn-stat: wac1_threshold=%zu\n", c.wac1_threshold);
   printf("%%%%%%mzn-stat: seed=%zu\n", c.seed);
   printf("%%%%%%mzn-stat: eps_var_order=\"%s\"\n", c.eps_var_order.c_str());
   printf("%%%%%%mzn-stat: eps_value_order=\"%s\"\n", c.eps_value_order.c_str());
@@ -301,8 +303,6 @@ int main(int argc, char** argv) {
   }
   if (config.arch != "barebones" && config.verbose)
     printf("%% WARNING: -arch %s is served by the barebones dive-and-solve architecture.\n", config.arch.c_str());
-  if (config.print_intermediate_solutions)
-    printf("%% WARNING: -arch barebones is incompatible with -i and -a (it cannot print intermediate solutions).\n");
 
   // ---- preprocessing (CP::preprocess, common_solving.hpp:605-637) ----------------------------------------
   tb_model* model = nullptr;
@@ -356,6 +356,7 @@ int main(int argc, char** argv) {
   tb_stats total;
   memset(&total, 0, sizeof(total));
   total.exhaustive = 1;
+  total.fixpoint_in_effect = config.fixpoint == "ac1" ? TB_FP_AC1 : config.fixpoint == "ac1_active" ? TB_FP_AC1_ACTIVE : config.fixpoint == "wac1_active" ? TB_FP_WAC1_ACTIVE : TB_FP_WAC1;
   const int okind = tb_model_objective_kind(model);
   if (tb_model_root_failed(model)) {                      // barebones :474-478
     print_final_separator(total);
@@ -382,7 +383,9 @@ int main(int argc, char** argv) {
     auto make = [&](int g) {
       tb_options o;
       memset(&o, 0, sizeof(o));
-      o.fixpoint = config.fixpoint == "ac1" ? TB_FP_AC1 : config.fixpoint == "ac1_active" ? TB_FP_AC1_ACTIVE : config.fixpoint == "wac1_active" ? TB_FP_WAC1_ACTIVE : TB_FP_WAC1;
+      // default: the active-set kind (same fixpoints and search tree, 1.7 x the nodes/s on the large networks); the engine
+      // itself runs the plain sweeps where tracking does not pay (small tables, store outside shared memory)
+      o.fixpoint = config.fixpoint == "ac1" ? TB_FP_AC1 : config.fixpoint == "ac1_active" ? TB_FP_AC1_ACTIVE : config.fixpoint == "wac1" ? TB_FP_WAC1 : TB_FP_WAC1_ACTIVE;
       o.wac1_threshold = (int32_t)config.wac1_threshold;
       o.subproblems_power = config.subproblems_power;
       o.subproblems_factor = (int32_t)config.subproblems_factor;
@@ -446,6 +449,50 @@ int main(int argc, char** argv) {
   if (config.verbose) printf("%% GPU kernel started, starting solving...\n");
   const int64_t kernel_start_ns = since_ns();
   if (config.verbose) printf("%% start-up: preprocessing (parse, ternarise, simplify on the GPU) %.3f s, engine creation %.3f s\n", to_sec(init_ns), to_sec(kernel_start_ns - init_ns));
+  // -i / -a: improving solutions are printed as they are found (the reference's barebones architecture cannot,
+  // barebones :465-467; its `gpu` architecture does it with a consumer thread, gpu_dive_and_solve.hpp:100-132)
+  std::atomic<bool> search_over{false};
+  std::mutex print_mutex;
+  bool printed_any = false;
+  int32_t last_printed = 0;                 // objective (of the minimised TNF variable) of the latest printed solution
+  std::vector<int32_t> plb(nv), pub(nv);
+  auto print_if_improving = [&](const int32_t* lb, const int32_t* ub, int32_t objective) {
+    std::lock_guard<std::mutex> lock(print_mutex);
+    if (printed_any && (pb->obj_var < 0 || objective >= last_printed)) return false;
+    int bad = tb_model_check_solution(model, lb, ub);
+    if (bad < 0) bad = tb_model_check_tnf(model, lb);
+    if (bad != 0) { std::cerr << "% ERROR: an intermediate solution violates " << bad << " constraint(s)" << std::endl; return false; }
+    size_t n = tb_model_format_solution(model, lb, ub, nullptr, 0);
+    std::string text(n + 1, '\0');
+    tb_model_format_solution(model, lb, ub, &text[0], n + 1);
+    fputs(text.c_str(), stdout);
+    printf("----------\n");
+    fflush(stdout);
+    printed_any = true; last_printed = objective;
+    return true;
+  };
+  std::thread consumer;
+  if (config.print_intermediate_solutions) {
+    for (int g = 0; g < G; ++g)
+      if (tb_stream_solutions(solvers[(size_t)g], 16) != TB_OK) { std::cerr << "tb_stream_solutions: " << tb_last_error() << std::endl; return EXIT_FAILURE; }
+    consumer = std::thread([&]() {
+      for (;;) {
+        const bool last_round = search_over.load();
+        bool got = false;
+        for (int g = 0; g < G; ++g) {
+          int32_t obj = 0;
+          while (tb_poll_solution(solvers[(size_t)g], plb.data(), pub.data(), &obj, nullptr) == 1) { got = true; print_if_improving(plb.data(), pub.data(), obj); }
+        }
+        if (last_round) break;
+        if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(2));
+      }
+    });
+  }
+  if (config.timeout_ms) {
+    // what is left of -t now that the engines exist (their creation overlapped on G host threads but is not free)
+    const int64_t left = (int64_t)config.timeout_ms - since_ns() / 1000000;
+    for (int g = 0; g < G; ++g) tb_set_timeout(solvers[(size_t)g], (uint64_t)std::max<int64_t>(1, left));
+  }
   {
     std::vector<std::thread> th;
     for (int g = 0; g < G; ++g)
@@ -455,6 +502,8 @@ int main(int argc, char** argv) {
       });
     for (auto& t : th) t.join();
   }
+  search_over.store(true);
+  if (consumer.joinable()) consumer.join();
   int exit_code = 0;
   for (int g = 0; g < G; ++g)
     if (rcs[(size_t)g] != TB_OK) { std::cerr << "tb_solve failed on GPU " << g << ": " << cerr_solve[(size_t)g] << std::endl; exit_code = EXIT_FAILURE; }
@@ -486,11 +535,15 @@ int main(int argc, char** argv) {
       std::cerr << "% ERROR: the solution violates " << bad << " constraint(s): " << tb_last_error() << std::endl;
       exit_code = 2;
     }
-    size_t n = tb_model_format_solution(model, lb, ub, nullptr, 0);
-    std::string text(n + 1, '\0');
-    tb_model_format_solution(model, lb, ub, &text[0], n + 1);
-    fputs(text.c_str(), stdout);
-    printf("----------\n");
+    // (with -i / -a the best solution has usually been printed already, when it was found)
+    const bool already = config.print_intermediate_solutions && printed_any && (pb->obj_var < 0 || lb[(size_t)pb->obj_var] >= last_printed);
+    if (!already) {
+      size_t n = tb_model_format_solution(model, lb, ub, nullptr, 0);
+      std::string text(n + 1, '\0');
+      tb_model_format_solution(model, lb, ub, &text[0], n + 1);
+      fputs(text.c_str(), stdout);
+      printf("----------\n");
+    }
   }
   print_final_separator(total);
   if (config.print_statistics) {

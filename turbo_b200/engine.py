@@ -240,6 +240,33 @@ class Solver:
         buf = C.create_string_buffer(blob, len(blob))
         _check(lib().tb_import_peer_bounds(self._h, C.cast(buf, C.c_void_p), len(handles)))
 
+    def stream_solutions(self, slots=16):
+        """-i / -a: improving solutions also go to a ring the host can read while solve() runs (tb_stream_solutions)."""
+        L = lib()
+        L.tb_stream_solutions.argtypes = [C.c_void_p, C.c_int32]
+        L.tb_stream_solutions.restype = C.c_int
+        _check(L.tb_stream_solutions(self._h, slots))
+
+    def poll_solution(self):
+        """The newest streamed solution not returned yet, or None (call from another thread while solve() blocks)."""
+        L = lib()
+        i32p = C.POINTER(C.c_int32)
+        L.tb_poll_solution.argtypes = [C.c_void_p, i32p, i32p, i32p, C.POINTER(C.c_int64)]
+        L.tb_poll_solution.restype = C.c_int32
+        n = self.problem.nvars
+        lb, ub = np.zeros(max(1, n), np.int32), np.zeros(max(1, n), np.int32)
+        obj, t = C.c_int32(0), C.c_int64(0)
+        rc = L.tb_poll_solution(self._h, _p(lb), _p(ub), C.byref(obj), C.byref(t))
+        if rc < 0:
+            _check(-rc)
+        return None if rc == 0 else dict(lb=lb[:n], ub=ub[:n], objective=obj.value, time_ns=t.value)
+
+    def set_timeout(self, ms):
+        L = lib()
+        L.tb_set_timeout.argtypes = [C.c_void_p, C.c_uint64]
+        L.tb_set_timeout.restype = C.c_int
+        _check(L.tb_set_timeout(self._h, ms))
+
     def result_pack(self):
         """The latest solve() of this solver as bytes (tb_result_pack): what one rank contributes to the final gather."""
         L = lib()
