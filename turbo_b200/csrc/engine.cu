@@ -598,7 +598,20 @@ struct Ctx {
 #pragma unroll
       for (int u = 0; u < TBC_U; ++u) w.notent |= tbd::not_entailed_bits<CLS>(s[u]);
       w.ch += nwarps;
+#ifdef TB_PIN_PREFETCH
+      // `nxt` was requested at the end of the previous visit. A plain register copy is scheduled right behind that
+      // request (at the top of this visit), where it waits for the whole L2 round trip; a funnel shift by an opaque
+      // zero with the visit's last result as its other operand is the same copy, but cannot issue before the visit
+      // is over: the request gets one whole visit to complete.
+#pragma unroll
+      for (int u = 0; u < TBC_U; ++u) {
+        const unsigned lo = __funnelshift_r((unsigned)w.nxt.w[u], (unsigned)w.notent, (unsigned)P.zero);
+        const unsigned hi = __funnelshift_r((unsigned)(w.nxt.w[u] >> 32), (unsigned)w.notent, (unsigned)P.zero);
+        w.cur.w[u] = ((unsigned long long)hi << 32) | lo;
+      }
+#else
       w.cur = w.nxt;
+#endif
       w.nxt = load_words(h.words, w.widx);
       w.widx += stride;
     } while (w.ch < ce);
@@ -1511,6 +1524,39 @@ static tb_status dev_alloc(tb_solver* s, T** p, size_t count) {
   return TB_OK;
 }
 
+// Cell blocks (engine_internal.h) are plain cudaMalloc allocations (CUDA IPC cannot export pool memory), and cudaFree
+// synchronises the device and costs tens of milliseconds: a destroyed solver's block goes to a per-device free list
+// instead and serves the next solver (the drop-in call pattern creates and destroys one solver per model).
+static std::mutex g_cells_mutex;
+static std::vector<unsigned long long*> g_free_cells[64];
+static unsigned long long* acquire_cells(int device) {
+  {
+    std::lock_guard<std::mutex> lock(g_cells_mutex);
+    if (device >= 0 && device < 64 && !g_free_cells[device].empty()) {
+      unsigned long long* p = g_free_cells[device].back();
+      g_free_cells[device].pop_back();
+      return p;
+    }
+  }
+  unsigned long long* p = nullptr;
+  if (cudaMalloc((void**)&p, TB_CELL_WORDS * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+static void release_cells(int device, unsigned long long* p) {
+  if (!p) return;
+  if (device < 0 || device >= 64) { cudaFree(p); return; }
+  std::lock_guard<std::mutex> lock(g_cells_mutex);
+  g_free_cells[device].push_back(p);
+}
+
+// TB_TRACE_TIMING=1: where tb_create / tb_destroy spend their time (stderr)
+struct PhaseTimer {
+  bool on; double t0; const char* what;
+  static double now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+  explicit PhaseTimer(const char* w) : on(getenv("TB_TRACE_TIMING") != nullptr), t0(now()), what(w) {}
+  void mark(const char* phase) { if (on) { const double t = now(); fprintf(stderr, "[tb timing] %s: %s %.3f ms\n", what, phase, t - t0); t0 = t; } }
+};
+
 // One pinned word holding the constant 1 (source of the asynchronous "stop" copy), shared by all solvers.
 static int32_t* pinned_one() {
   static int32_t* p = nullptr;
@@ -1773,6 +1819,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     for (int j = 0; j < st.n; ++j) if (st.vars[j] < 0 || st.vars[j] >= pb->nvars) { set_error("strategy variable out of range"); return TB_ERR_INVALID; }
   }
   if (tb_device_count() <= 0) { set_error("no CUDA device visible: the engine has no CPU fallback"); return TB_ERR_NO_DEVICE; }
+  PhaseTimer pt("tb_create");
 
   tb_options opt;
   memset(&opt, 0, sizeof(opt));
@@ -1820,7 +1867,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   // trains15, 420 chunks: 5.7 M dense, 8.4 M active): below TB_ACTIVE_MIN_CHUNKS (default 128) the plain kind runs
   // and no flag area is reserved. Chunk ids must fit the 16-bit fields of the watch words.
   if (P.nchunks < env_int("TB_ACTIVE_MIN_CHUNKS", 128) || P.nchunks >= 0xFFFE) s->want_active = false;
+  pt.mark("validate, classify");
   if ((rc = configure(s)) != TB_OK) return fail(rc);
+  pt.mark("configure");
   {
     TnfLayoutOptions lo;
     const bool shared_store = s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED;
@@ -1838,8 +1887,10 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     if (pb->obj_var >= 0) P.obj_var = L.slot_of[pb->obj_var];
     for (int v = 0; v < pb->nvars; ++v) if (L.referenced[v] && pb->lb[v] > pb->ub[v]) P.root_failed = 1;
   }
+  pt.mark("layout pass");
   place_active(s);
   if ((rc = set_smem_attr(s)) != TB_OK) return fail(rc);
+  pt.mark("kernel attributes, occupancy");
 
   // ---- device images ---------------------------------------------------------------------------------
   {
@@ -1914,13 +1965,15 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   {
     unsigned long long init[TB_CELL_WORDS] = {0};
     init[TB_CELL_BOUND] = ~0ull;            // epoch 0, no incumbent
-    if (cudaMalloc((void**)&s->d_cells, sizeof(init)) != cudaSuccess ||
+    if ((s->d_cells = acquire_cells(s->device)) == nullptr ||
         cudaMemcpy(s->d_cells, init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("cudaMalloc (grid cells) failed"); cudaGetLastError(); return fail(TB_ERR_CUDA);
     }
   }
   P.cells = s->d_cells; P.npeers = 0; P.steal = 0; P.epoch = 0; P.observe_stop = 1;
+  pt.mark("uploads");
   if ((rc = ensure_scratch(s, s->num_blocks))) return fail(rc);
+  pt.mark("per-block scratch");
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&s->ev_start) != cudaSuccess || cudaEventCreate(&s->ev_stop) != cudaSuccess ||
@@ -1958,6 +2011,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     const unsigned long long want = (unsigned long long)opt.subproblems_factor * (unsigned long long)s->num_blocks * (unsigned long long)opt.gpu_world;
     while ((1ull << d) < want && d < 62) ++d;
   }
+  pt.mark("streams, L2 window");
   if (d > TB_K_BITS) d = TB_K_BITS;          // the dispenser word keeps its high bits for the epoch
   P.subproblems_power = d;
   P.num_subproblems = 1ull << d;
@@ -1967,11 +2021,15 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
 
 extern "C" void tb_destroy(tb_solver* s) {
   if (!s) return;
+  PhaseTimer pt("tb_destroy");
   cudaSetDevice(s->device);
   for (void* h : s->ipc_opened) cudaIpcCloseMemHandle(h);
+  pt.mark("ipc close");
   if (s->stream) cudaStreamSynchronize(s->stream);
+  pt.mark("stream sync");
   for (void* p : s->allocs) cudaFreeAsync(p, (cudaStream_t)0);     // back to the pool, which keeps it
-  if (s->d_cells) cudaFree(s->d_cells);
+  pt.mark("free async");
+  release_cells(s->device, s->d_cells);
   cudaGetLastError();
   if (s->poll_stream) cudaStreamDestroy(s->poll_stream);
   if (s->h_stream_rec) cudaFreeHost(s->h_stream_rec);
@@ -1980,7 +2038,9 @@ extern "C" void tb_destroy(tb_solver* s) {
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->ev_start) cudaEventDestroy(s->ev_start);
   if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+  pt.mark("streams, events");
   delete s;
+  pt.mark("delete");
 }
 
 static void fill_config(const tb_solver* s, tb_stats* st) {

@@ -25,12 +25,17 @@ __global__ void __launch_bounds__(kThreads) smem_stream_kernel(int iters, unsign
   // iteration are independent (fixed addresses 2 KB apart, immediate offsets: no address arithmetic in the loop)
   const unsigned a = (unsigned)__cvta_generic_to_shared(store) + (threadIdx.x & 31) * 8u + ((threadIdx.x >> 5) & 7) * 256u;
   int acc0 = 0, acc1 = 0;
+  __syncthreads();
+  const long long c0 = clock64();
   for (int it = 0; it < iters; ++it) {
 #define TB_LD(K) { int x, y; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2+" #K "];" : "=r"(x), "=r"(y) : "r"(a)); acc0 ^= x; acc1 += y; }
     TB_LD(0) TB_LD(2048) TB_LD(4096) TB_LD(6144) TB_LD(8192) TB_LD(10240) TB_LD(12288) TB_LD(14336)
     TB_LD(16384) TB_LD(18432) TB_LD(20480) TB_LD(22528) TB_LD(24576) TB_LD(26624) TB_LD(28672) TB_LD(30720)
 #undef TB_LD
   }
+  __syncthreads();
+  const long long c1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[1] = (unsigned long long)(c1 - c0);   // SM cycles of the stream, one CTA's view
   if ((acc0 ^ acc1) == 0x7fffffff) out[0] = (unsigned long long)acc0;     // never true: keeps the loads alive
 }
 
@@ -71,9 +76,11 @@ extern "C" tb_status tb_measure_smem_peak(int32_t device, double* gb_per_s, doub
   if (rc == TB_OK) {
     const double bytes = (double)grid * kThreads * (double)iters * 16.0 * 8.0;
     *gb_per_s = bytes / (best_ms * 1e-3) / 1e9;
-    int khz = 0;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
-    if (bytes_per_clk_per_sm) *bytes_per_clk_per_sm = khz > 0 ? bytes / (best_ms * 1e-3) / ((double)khz * 1e3) / dp.multiProcessorCount : 0.0;
+    // bytes per clock per SM from the SM's own cycle counter (no assumption about the clock the launch ran at): the
+    // CTAs resident on block 0's SM moved per_sm * kThreads * iters * 128 B in the cycles block 0 counted
+    unsigned long long h[2] = {0, 0};
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    if (bytes_per_clk_per_sm) *bytes_per_clk_per_sm = h[1] ? (double)per_sm * kThreads * (double)iters * 16.0 * 8.0 / (double)h[1] : 0.0;
   } else {
     tb_set_error_internal("smem peak: kernel failed"); cudaGetLastError();
   }
