@@ -465,6 +465,82 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+REPORT_CONFIGS = {"1": "simplified:example_wordpress7_500", "2": "simplified:trains15", "3": "simplified:accap_a3"}
+
+
+def run_report(args):
+    """CPU-1, CPU-N and GPU-N back to back on the same TNF with the same wall budget, one table
+    (`include/cpu_solving.hpp:8-48` is the shape of the CPU legs; the reference binary cannot be built, so they are the
+    oracle port). Under torchrun every rank takes part in the GPU leg (sharded subproblems, shared incumbent, NCCL
+    gather of the results); rank 0 alone runs the CPU legs and prints. One JSON line per leg, then the table."""
+    import torch
+    from turbo_b200 import engine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    budget = args.report_ms
+    cores = os.cpu_count() or 1
+    rows = []
+    for key in args.report.split(","):
+        wl = REPORT_CONFIGS.get(key, key)
+        pb, info = load_workload(wl)
+        objective = lambda lb, ub: golden_io.user_objective(info, lb, ub) if info.get("objective_kind", -1) >= 0 else None
+
+        def row(leg, r, st, secs, n):
+            d = {"config": key, "workload": wl, "leg": leg, "workers": n, "budget_ms": budget,
+                 "status": ("optimal" if r["exhaustive"] else "feasible") if r["has_solution"] else ("unsatisfiable" if r["exhaustive"] else "unknown"),
+                 "objective": objective(r["lb"], r["ub"]) if r["has_solution"] else None, "nodes": st["nodes"],
+                 "propagations": st["num_deductions"], "fixpoint_iterations": st["fixpoint_iterations"], "wall_s": secs,
+                 "nodes_per_sec": st["nodes"] / secs, "propagations_per_sec": st["num_deductions"] / secs,
+                 "time_to_best_s": st["timers_ns"][abi.TIMER_LATEST_BEST_OBJ_FOUND] / 1e9}
+            rows.append(d)
+            print(json.dumps(d), flush=True)
+
+        if rank == 0 and not args.report_no_cpu:
+            from oracle import oracle_py as orc
+            for n in (1, cores):
+                t = time.perf_counter()
+                r = orc.solve(pb, depth=min(12, 20), timeout_ms=budget, nthreads=n)
+                row(f"CPU-{n} (oracle port)", r, r["stats"], time.perf_counter() - t, n)
+        if dist is not None:
+            dist.barrier()
+        for fp in ("wac1", "wac1_active"):
+            s = engine.Solver(pb, device=local, gpu_rank=rank, gpu_world=world, timeout_ms=budget, fixpoint=abi.FP_KINDS[fp])
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, s.export_bound_handle())
+                s.import_peer_bounds([h for q, h in enumerate(handles) if q != rank])
+                dist.barrier()
+            t = time.perf_counter()
+            s.solve()
+            secs = time.perf_counter() - t
+            if world > 1:
+                mine = torch.from_numpy(s.result_pack()).cuda()
+                got = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+                dist.gather(mine, got, dst=0)
+                m = engine.result_reduce([g.cpu().numpy() for g in got]) if rank == 0 else None
+            else:
+                m = engine.result_reduce([s.result_pack()])
+            cfg = s.config()
+            s.close()
+            if rank == 0:
+                row(f"GPU-{world} ({fp}, {abi.MEM_NAMES.get(cfg['mem_kind'])})", m, m["stats"], secs, world)
+    if rank == 0:
+        print("\n| config | leg | status | objective | nodes | nodes/s | propagations/s | time to best (s) | wall (s) |")
+        print("|---|---|---|---|---|---|---|---|---|")
+        for d in rows:
+            print(f"| {d['config']} {d['workload']} | {d['leg']} | {d['status']} | {d['objective']} | {d['nodes']} | {d['nodes_per_sec']:.3g} | "
+                  f"{d['propagations_per_sec']:.3g} | {d['time_to_best_s']:.2f} | {d['wall_s']:.1f} |")
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -485,8 +561,13 @@ def main():
     ap.add_argument("--mem", default="auto", choices=["auto", "global", "store_shared", "tcn_shared", "store_cluster"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixpoint-leg", action="store_true")
+    ap.add_argument("--report", default=None, help="BASELINE.md §3 table instead of the bench line: comma list of configs (1 = wordpress7_500, 2 = trains15, 3 = accap_a3, or a workload name)")
+    ap.add_argument("--report-ms", type=int, default=20000, help="wall budget of every leg of --report (the reference's -t 20000)")
+    ap.add_argument("--report-no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.report:
+        run_report(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

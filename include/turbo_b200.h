@@ -166,7 +166,7 @@ tb_status tb_solve(tb_solver*, volatile int32_t* stop_flag,
 /* Intermediate solutions (-i / -a; the reference's consumer thread, gpu_dive_and_solve.hpp:100-132; its barebones
  * architecture cannot, barebones_dive_and_solve.hpp:465-467).  tb_stream_solutions (before tb_solve) makes every
  * improving solution also land in a ring of `slots` store images; tb_poll_solution, called from ANOTHER host thread
- * while tb_solve blocks (no callbacks into the host), hands out the newest solution not handed out yet: returns 1 and
+ * while tb_solve blocks (no callbacks into the host), hands out the oldest solution not handed out yet: returns 1 and
  * fills lb / ub / objective (of the minimised variable) / time_ns (since the search started), 0 when there is none,
  * a negative tb_status on error.  A consumer slower than `slots` solutions misses intermediate ones, never the last. */
 tb_status tb_stream_solutions(tb_solver*, int32_t slots);

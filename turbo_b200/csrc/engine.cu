@@ -86,6 +86,29 @@ __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- tensor memory as a table cache ----------------------------------------------------------------------------
+// The fixpoint never touches the tensor cores, so the SM's 256 KB of tensor memory (512 columns x 128 lanes x 32 bit)
+// are free. A warp can reach the 32 lanes of its quarter (warp index mod 4) at any column: lane l of the warp keeps
+// ITS propagator word of visit k in columns 2k, 2k+1 of its own TMEM lane. tcgen05.st fills them once per launch,
+// one tcgen05.ld per visit reads them back with a latency of a dozen cycles instead of an L2 round trip, and the
+// table stream leaves the L2 -> SM path altogether.
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_st64(unsigned taddr, unsigned long long v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"((unsigned)v), "r"((unsigned)(v >> 32)) : "memory");
+}
+__device__ __forceinline__ unsigned long long tmem_ld64(unsigned taddr) {
+  unsigned lo, hi;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return ((unsigned long long)hi << 32) | lo;
+}
+
 // The bulk-copy unit takes sizes that are multiples of 16 B; one instruction moves at most this
 // many bytes so that the mbarrier transaction count (20 bits) never overflows.
 #define BULK_CHUNK (128u * 1024u)
@@ -113,7 +136,9 @@ struct Ctl {                       // per-CTA control block in static shared mem
   int pushed;
   int dirty_all;                   // active-set fixpoint: the store was rewritten, every chunk must be evaluated
   long long t_mark;
+  unsigned tmem_base;              // tensor-memory address of the CTA's columns (tcgen05.alloc writes it here)
   unsigned long long stream_seq;   // number of the solution being streamed (tb_stream_solutions)
+  int stream_slot;                 // and the ring slot it goes to
 };
 
 // The block store: one {lb, ub} pair of int32 per slot.  All accesses are volatile inline PTX on explicit
@@ -235,6 +260,8 @@ struct Ctx {
   unsigned char* sdyn;     // dynamic shared memory: the store image of this CTA (shared placements)
   const unsigned long long* words;   // the propagator table: global (L2) or shared (TCN_SHARED)
   unsigned mbar_phase;
+  unsigned tm_warp;        // tensor-memory address of this warp's table words (tm_visits of them; 0 = none)
+  int tm_visits;
   unsigned fp_rot;         // rotation of the three fixpoint flag words, kept across calls (fixpoint3)
   int sel_par;             // which selection cell the next split() uses
   unsigned narrowed;       // per-thread count of published bounds
@@ -390,6 +417,8 @@ struct Ctx {
     StoreRef<MEM> store;
     const unsigned long long* words;
     unsigned narrowed;
+    unsigned tm;               // tensor-memory address of this warp's first word (column of visit 0)
+    int tm_visits;             // visits served from tensor memory (0 = none)
   };
 
   struct Walk {
@@ -548,7 +577,17 @@ struct Ctx {
     unsigned pad_evals;           // propagator evaluations spent on padding lanes
     int changed;                  // some visit published a bound
     int notent;                   // per lane: non-zero iff some propagator of this lane is not entailed
+    int tk;                       // visit number of the next request (which tensor-memory columns hold its words)
   };
+
+  // The words of the chunk a warp visits `tk` visits into its sweep: from tensor memory when they are there.
+  __device__ __forceinline__ Words next_words(const Hot& h, Walk3& w) const {
+    Words r;
+    if (TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && w.tk < h.tm_visits) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
+    else r = load_words(h.words, w.widx);
+    ++w.tk;
+    return r;
+  }
 
   // Returns true when the store failed (the sweep is over for this warp).
   template <int CLS>
@@ -612,7 +651,7 @@ struct Ctx {
 #else
       w.cur = w.nxt;
 #endif
-      w.nxt = load_words(h.words, w.widx);
+      w.nxt = next_words(h, w);
       w.widx += stride;
     } while (w.ch < ce);
     // the class's last chunk is padded with copies of its last propagator: do not count those lanes
@@ -626,6 +665,7 @@ struct Ctx {
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
     Hot h;
     h.store = store; h.words = words; h.narrowed = narrowed;
+    h.tm = tm_warp; h.tm_visits = tm_visits;
     unsigned long long ded = 0;
     unsigned rot = fp_rot;
     int it = 0, f;
@@ -633,9 +673,10 @@ struct Ctx {
       Walk3 w;
       w.ch = warp; w.extra = w.pad_evals = 0; w.changed = 0; w.notent = 0;
       w.widx = (warp * 32 + lane) * TBC_U;
-      w.cur = load_words(h.words, w.widx);
+      w.tk = 0;
+      w.cur = next_words(h, w);
       w.widx += stride;
-      w.nxt = load_words(h.words, w.widx);
+      w.nxt = next_words(h, w);
       w.widx += stride;
       bool failed = false;
 #define TB_SWEEP(CLS) if (!failed && w.ch < P.cls_begin[CLS + 1]) failed = sweep_class3<CLS>(h, w, wac1, nwarps, stride);
@@ -832,13 +873,21 @@ struct Ctx {
   // An improving solution also goes into a ring of images the host reads WHILE the kernel runs (tb_poll_solution from
   // another host thread; the reference's consumer thread, gpu_dive_and_solve.hpp:100-132): the image first, then a
   // record in pinned host memory whose sequence number is written last. A slot is reused after stream_slots more
-  // solutions; a consumer that lags that far simply misses intermediate solutions (it re-checks the record).
+  // solutions; a consumer that lags that far simply misses intermediate solutions (it re-checks the record). A slot
+  // has one writer at a time (several blocks may find their first solutions in the same microsecond): a lock per slot,
+  // taken by walking the ring from the solution's own slot to the first free one.
   __device__ __forceinline__ void stream_solution(int objective) {
-    if (tid == 0) c.stream_seq = atomicAdd(P.cells + TB_CELL_STREAM, 1ull);
+    if (tid == 0) {
+      const unsigned long long q = atomicAdd(P.cells + TB_CELL_STREAM, 1ull);
+      int s0 = (int)(q % (unsigned long long)P.stream_slots);
+      while (atomicCAS(P.stream_lock + s0, 0, 1) != 0) s0 = s0 + 1 == P.stream_slots ? 0 : s0 + 1;
+      c.stream_seq = q; c.stream_slot = s0;
+      P.stream_rec[s0].seq = 0ull;                  // the slot is being rewritten
+      __threadfence_system();
+    }
     sync();
     const unsigned long long seq = c.stream_seq;
-    const int sl = (int)(seq % (unsigned long long)P.stream_slots);
-    if (tid == 0) { P.stream_rec[sl].seq = 0ull; __threadfence_system(); }      // the slot is being rewritten
+    const int sl = c.stream_slot;
     save_store(P.stream_img + (size_t)sl * 2 * P.vpad);
     if (threadIdx.x == 0) bulk_wait_all();
     __threadfence_system();
@@ -849,6 +898,7 @@ struct Ctx {
       __threadfence_system();
       *(volatile unsigned long long*)&r->seq = seq + 1ull;
       __threadfence_system();
+      atomicExch(P.stream_lock + sl, 0);
     }
   }
 
@@ -1270,6 +1320,25 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
     for (int i = threadIdx.x; i < words_; i += blockDim.x) a[i] = 0u;
   }
   k.sync();
+  k.tm_warp = 0; k.tm_visits = 0;
+  if (MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && P.tmem_cols) {
+    // the table goes to tensor memory: one warp allocates the CTA's columns, every warp stores the words of its own
+    // first tmem_visits visits into its quarter of the lanes (chunk ch = warp + k * nwarps at columns 2k, 2k + 1)
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31), nwarps = (int)(blockDim.x >> 5);
+    if (warp == 0) tmem_alloc(&local->tmem_base, (unsigned)P.tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    k.sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned cols_per_warp = (unsigned)P.tmem_cols / (unsigned)((nwarps + 3) / 4);
+    k.tm_warp = local->tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(warp >> 2) * cols_per_warp;
+    k.tm_visits = P.tmem_visits;
+    for (int v = 0; v < P.tmem_visits; ++v) {
+      const int ch = warp + v * nwarps;
+      // (the table is padded behind its end: a chunk index past nchunks reads zeros that are never evaluated)
+      tmem_st64(k.tm_warp + 2u * (unsigned)v, __ldg(P.words + (size_t)ch * 32 + lane));
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
   if (MEM == TB_MEM_TCN_SHARED) {
     // stage the propagator table once: TMA bulk copy global -> shared
     unsigned char* sprops = dyn + store_bytes;
@@ -1296,6 +1365,8 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
   }
   if (threadIdx.x == 0) bulk_wait_all();     // images still on their way to global memory (best store, snapshots)
   k.sync();        // with a cluster: nobody leaves while a peer may still touch its shared memory
+  if (MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && k.P.tmem_cols && threadIdx.x < 32)
+    tmem_dealloc(k.lc->tmem_base, (unsigned)k.P.tmem_cols);
 }
 
 // ================================================================================================
@@ -1607,6 +1678,20 @@ static cudaError_t launch_workers(const tb_solver* s, void (*kernel)(KArgs...), 
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaGetDeviceProperties costs 10-20 ms a call: asked once per device
+static const cudaDeviceProp* device_props(int device) {
+  static cudaDeviceProp props[64];
+  static bool have[64] = {false};
+  static std::mutex m;
+  if (device < 0 || device >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(m);
+  if (!have[device]) {
+    if (cudaGetDeviceProperties(&props[device], device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    have[device] = true;
+  }
+  return &props[device];
+}
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -1622,8 +1707,9 @@ static int pow2_threads(int t) {
 // Placement policy: MemoryConfig (memory_gpu.hpp:43-84) + configure_gpu_barebones (barebones :527-606),
 // solved together with occupancy (the reference queries occupancy with 0 dynamic smem).
 static tb_status configure(tb_solver* s) {
-  cudaDeviceProp dp;
-  CU(cudaGetDeviceProperties(&dp, s->device));
+  const cudaDeviceProp* dpp = device_props(s->device);
+  if (!dpp) { set_error("cudaGetDeviceProperties failed"); return TB_ERR_CUDA; }
+  const cudaDeviceProp& dp = *dpp;
   s->num_sms = dp.multiProcessorCount;
   const size_t max_block_smem = dp.sharedMemPerBlockOptin;               // 227 KB on sm_100
   const size_t sm_smem = dp.sharedMemPerMultiprocessor;                  // 228 KB
@@ -1890,6 +1976,16 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   pt.mark("layout pass");
   place_active(s);
   if ((rc = set_smem_attr(s)) != TB_OK) return fail(rc);
+  // Tensor memory as the table cache (STORE_SHARED, dense kinds): the resident CTAs of an SM share its 512 columns, a
+  // CTA's warps share the CTA's columns by quarter (warp index mod 4), a visit takes two columns. TB_TMEM=0: off.
+  P.tmem_cols = 0; P.tmem_visits = 0;
+  if (TBC_U == 1 && s->mem_kind == TB_MEM_STORE_SHARED && !s->active && env_int("TB_TMEM", 1) != 0 && P.nchunks > 0) {
+    int cols = 32;
+    while (cols * 2 * s->blocks_per_sm <= 512) cols *= 2;
+    const int nwarps = s->threads / 32, per_quarter = (nwarps + 3) / 4;
+    const int visits_fit = cols / per_quarter / 2, visits_needed = (P.nchunks + nwarps - 1) / nwarps;
+    if (cols * s->blocks_per_sm <= 512 && visits_fit >= 1) { P.tmem_cols = cols; P.tmem_visits = std::min(visits_fit, visits_needed); }
+  }
   pt.mark("kernel attributes, occupancy");
 
   // ---- device images ---------------------------------------------------------------------------------
@@ -1982,11 +2078,13 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   }
 
   // The propagator table is what every block streams from L2 in every sweep, next to the snapshot images that flow
-  // through L2 once: ask for the table's lines to persist (access policy window on the solver's stream; TB_L2_PERSIST=0
-  // turns it off). Best effort: a device without the feature just keeps its normal policy.
-  if (env_int("TB_L2_PERSIST", 1) != 0 && s->mem_kind != TB_MEM_TCN_SHARED && s->layout.words.size()) {
-    cudaDeviceProp dp;
-    if (cudaGetDeviceProperties(&dp, s->device) == cudaSuccess && dp.persistingL2CacheMaxSize > 0 && dp.accessPolicyMaxWindowSize > 0) {
+  // through L2 once: TB_L2_PERSIST=1 asks for the table's lines to persist (access policy window on the solver's stream). Best effort: a device without the feature just keeps its normal policy.
+  // Measured (profiles/r02_ab_dense_variants.md): no effect on the solve kernel (320.6 against 320.8 Gprop/s: the table
+  // never leaves L2 anyway) and 30-110 ms per tb_create for the two API calls, so it is OFF unless TB_L2_PERSIST=1.
+  if (env_int("TB_L2_PERSIST", 0) != 0 && s->mem_kind != TB_MEM_TCN_SHARED && s->layout.words.size()) {
+    const cudaDeviceProp* dpp = device_props(s->device);
+    if (dpp && dpp->persistingL2CacheMaxSize > 0 && dpp->accessPolicyMaxWindowSize > 0) {
+      const cudaDeviceProp& dp = *dpp;
       const size_t bytes = std::min<size_t>(s->layout.words.size() * 8, (size_t)dp.accessPolicyMaxWindowSize);
       size_t cur = 0;
       cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
@@ -2061,6 +2159,8 @@ extern "C" tb_status tb_stream_solutions(tb_solver* s, int32_t slots) {
   if (s->h_stream_rec) { set_error("tb_stream_solutions: already enabled"); return TB_ERR_INVALID; }
   tb_status rc;
   if ((rc = dev_alloc(s, &s->P.stream_img, (size_t)slots * 2 * (size_t)s->P.vpad))) return rc;
+  if ((rc = dev_alloc(s, &s->P.stream_lock, (size_t)TB_STREAM_MAX_SLOTS))) return rc;
+  CU(cudaMemset(s->P.stream_lock, 0, sizeof(int) * TB_STREAM_MAX_SLOTS));
   CU(cudaHostAlloc((void**)&s->h_stream_rec, sizeof(StreamRec) * (size_t)slots, cudaHostAllocMapped | cudaHostAllocPortable));
   CU(cudaHostAlloc((void**)&s->h_stream_img, sizeof(int) * 2 * (size_t)s->P.vpad, cudaHostAllocPortable));
   memset(s->h_stream_rec, 0, sizeof(StreamRec) * (size_t)slots);
@@ -2079,11 +2179,11 @@ extern "C" int32_t tb_poll_solution(tb_solver* s, int32_t* lb, int32_t* ub, int3
   if (!s->P.stream_slots || !s->h_stream_rec) return 0;
   if (cudaSetDevice(s->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return -TB_ERR_CUDA; }
   for (int attempt = 0; attempt < 4; ++attempt) {
-    // the newest record not handed out yet
-    int best = -1; unsigned long long best_seq = s->stream_read;
+    // the oldest record not handed out yet (solutions come out in the order they were found)
+    int best = -1; unsigned long long best_seq = ~0ull;
     for (int i = 0; i < s->P.stream_slots; ++i) {
       const unsigned long long q = *(volatile unsigned long long*)&s->h_stream_rec[i].seq;
-      if (q > best_seq) { best_seq = q; best = i; }
+      if (q > s->stream_read && q < best_seq) { best_seq = q; best = i; }
     }
     if (best < 0) return 0;
     StreamRec rec;
@@ -2205,6 +2305,7 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
     std::lock_guard<std::mutex> lock(s->poll_mutex);
     const unsigned long long z = 0;
     CU(cudaMemcpyAsync(s->d_cells + TB_CELL_STREAM, &z, sizeof(z), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(s->P.stream_lock, 0, sizeof(int) * TB_STREAM_MAX_SLOTS, s->stream));
     memset(s->h_stream_rec, 0, sizeof(StreamRec) * (size_t)P.stream_slots);
     s->stream_read = 0;
   }

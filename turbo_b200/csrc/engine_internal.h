@@ -93,7 +93,11 @@ struct DevParams {
   // intermediate solutions (tb_stream_solutions): ring of store images in device memory + records in mapped host memory
   int* stream_img;                       // [stream_slots] images of 2 * vpad ints
   StreamRec* stream_rec;                 // [stream_slots], pinned host memory
+  int* stream_lock;                      // [TB_STREAM_MAX_SLOTS] one writer per slot at a time
   int stream_slots, pad4_;
+  // the propagator table in TENSOR MEMORY (STORE_SHARED, dense kinds): the first tmem_visits visits of every warp read
+  // their words from the CTA's TMEM columns instead of L2; tmem_cols = columns the CTA allocates (0 = off)
+  int tmem_cols, tmem_visits;
   int act_off;                           // byte offset of the active-set area in dynamic shared memory
   int act_fpw;                           // chunk flags per warp (multiple of 32): chunk ch is flag (ch / nwarps) of warp (ch % nwarps)
 };
