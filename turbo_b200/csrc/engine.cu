@@ -92,6 +92,11 @@ __device__ __forceinline__ void bulk_wait_all() {
 // ITS propagator word of visit k in columns 2k, 2k+1 of its own TMEM lane. tcgen05.st fills them once per launch,
 // one tcgen05.ld per visit reads them back with a latency of a dozen cycles instead of an L2 round trip, and the
 // table stream leaves the L2 -> SM path altogether.
+#ifdef TB_NO_TMEM
+#define TB_TMEM_CODE 0
+#else
+#define TB_TMEM_CODE 1
+#endif
 __device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -583,7 +588,7 @@ struct Ctx {
   // The words of the chunk a warp visits `tk` visits into its sweep: from tensor memory when they are there.
   __device__ __forceinline__ Words next_words(const Hot& h, Walk3& w) const {
     Words r;
-    if (TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && w.tk < h.tm_visits) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
+    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && w.tk < h.tm_visits) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
     else r = load_words(h.words, w.widx);
     ++w.tk;
     return r;
@@ -1321,7 +1326,7 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   }
   k.sync();
   k.tm_warp = 0; k.tm_visits = 0;
-  if (MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && P.tmem_cols) {
+  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && P.tmem_cols) {
     // the table goes to tensor memory: one warp allocates the CTA's columns, every warp stores the words of its own
     // first tmem_visits visits into its quarter of the lanes (chunk ch = warp + k * nwarps at columns 2k, 2k + 1)
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31), nwarps = (int)(blockDim.x >> 5);
@@ -1365,7 +1370,7 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
   }
   if (threadIdx.x == 0) bulk_wait_all();     // images still on their way to global memory (best store, snapshots)
   k.sync();        // with a cluster: nobody leaves while a peer may still touch its shared memory
-  if (MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && k.P.tmem_cols && threadIdx.x < 32)
+  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && k.P.tmem_cols && threadIdx.x < 32)
     tmem_dealloc(k.lc->tmem_base, (unsigned)k.P.tmem_cols);
 }
 
@@ -1838,7 +1843,14 @@ static tb_status set_smem_attr(tb_solver* s) {
       // registers limit the resident CTAs too: ask the driver what really fits (persistent kernel: one wave)
       int per_sm = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<m, act>, s->threads, s->shared_bytes));
+      if (getenv("TB_TRACE_TIMING")) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, solve_kernel<m, act>) == cudaSuccess)
+          fprintf(stderr, "[tb config] solve_kernel<%d,%d>: %d threads, dynamic smem %zu, static smem %zu, %d registers, local %zu B -> %d CTAs per SM by the occupancy API (policy wanted %d)\n",
+                  m, (int)act, s->threads, s->shared_bytes, fa.sharedSizeBytes, fa.numRegs, fa.localSizeBytes, per_sm, s->blocks_per_sm);
+      }
       if (per_sm < 1) { set_error("the solve kernel does not fit on an SM with this configuration"); return TB_ERR_UNSUPPORTED; }
+      if (env_int("TB_IGNORE_OCCUPANCY_API", 0)) per_sm = std::max(per_sm, s->blocks_per_sm);
       if (per_sm < s->blocks_per_sm) {
         s->blocks_per_sm = per_sm;
         int blocks = per_sm * s->num_sms;
@@ -1979,7 +1991,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   // Tensor memory as the table cache (STORE_SHARED, dense kinds): the resident CTAs of an SM share its 512 columns, a
   // CTA's warps share the CTA's columns by quarter (warp index mod 4), a visit takes two columns. TB_TMEM=0: off.
   P.tmem_cols = 0; P.tmem_visits = 0;
-  if (TBC_U == 1 && s->mem_kind == TB_MEM_STORE_SHARED && !s->active && env_int("TB_TMEM", 1) != 0 && P.nchunks > 0) {
+  if (TB_TMEM_CODE && TBC_U == 1 && s->mem_kind == TB_MEM_STORE_SHARED && !s->active && env_int("TB_TMEM", 1) != 0 && P.nchunks > 0) {
     int cols = 32;
     while (cols * 2 * s->blocks_per_sm <= 512) cols *= 2;
     const int nwarps = s->threads / 32, per_quarter = (nwarps + 3) / 4;

@@ -16,10 +16,12 @@ void tb_set_error_internal(const char* s);
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr int kBytes = 128 * 1024;    // 16 K {lb, ub} pairs of dynamic shared memory: every warp streams its own 4 KB
+constexpr int kBytes = 136 * 1024;    // 17 K {lb, ub} pairs of dynamic shared memory (MODE 1: every warp streams its own 4 KB window and the next)
 
-// MODE 0: every load of a lane hits the same 16 addresses in every iteration (the first version of this benchmark;
-//         ncu counts 0.5 wavefronts per LDS.64 for it and the SM's cycle counter 3.6 x the nominal bandwidth);
+// (The "memory" clobber of the load matters: without it the compiler merges the identical loads of the iterations it
+// unrolls, one LDS per four counted - the first version of this benchmark reported 478 B/clk/SM that way; ncu's
+// instruction count gave it away.)
+// MODE 0: every load of a lane hits the same 16 addresses in every iteration;
 // MODE 1: warp w reads its own 4 KB window, lane l the l-th pair of a 256-byte row, the row advancing every load:
 //         32 warps x 16 rows of distinct addresses (a contiguous row stream: the hardware serves a 256-byte row wide);
 // MODE 2: a GATHER: the 16 lanes of a half-warp read 16 different 8-byte banks in 16 different 128-byte rows, the rows
@@ -36,13 +38,15 @@ __global__ void __launch_bounds__(kThreads) smem_stream_kernel(int iters, unsign
   // MODE 2: bank = lane mod 16 (8-byte banks), row = a per-lane pseudo-random 128-byte row; the 16 immediate offsets
   // below move every lane by whole rows, so the banks stay distinct within a half-warp
   const unsigned a = MODE == 0 ? base + lane * 8u + (warp & 7) * 256u
-                   : MODE == 1 ? base + warp * 4096u + lane * 8u
+                   : MODE == 1 ? base + warp * 4096u + lane * 8u + (blockIdx.x & 0u)
                                : base + (lane & 15) * 8u + (((lane * 37u + warp * 101u) & 511u) << 7);
   int acc0 = 0, acc1 = 0;
   __syncthreads();
   const long long c0 = clock64();
   for (int it = 0; it < iters; ++it) {
-#define TB_LD(K) { int x, y; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2+" #K "];" : "=r"(x), "=r"(y) : "r"(a)); acc0 ^= x; acc1 += y; }
+    // whole rows more every iteration (same banks): the compiler cannot merge the loads of the iterations it unrolls
+    const unsigned ai = MODE == 1 ? a + (((unsigned)it * 256u) & 0xF00u) : a + (((unsigned)it * 128u) & 0x780u);
+#define TB_LD(K) { int x, y; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2+" #K "];" : "=r"(x), "=r"(y) : "r"(ai) : "memory"); acc0 ^= x; acc1 += y; }
     if (MODE == 0) {
       TB_LD(0) TB_LD(2048) TB_LD(4096) TB_LD(6144) TB_LD(8192) TB_LD(10240) TB_LD(12288) TB_LD(14336)
       TB_LD(16384) TB_LD(18432) TB_LD(20480) TB_LD(22528) TB_LD(24576) TB_LD(26624) TB_LD(28672) TB_LD(30720)
