@@ -670,7 +670,8 @@ struct Ctx {
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
     Hot h;
     h.store = store; h.words = words; h.narrowed = narrowed;
-    h.tm = tm_warp; h.tm_visits = tm_visits;
+    // (broadcast from lane 0: the address is warp-uniform, tcgen05.ld takes it from a uniform register)
+    h.tm = __shfl_sync(0xffffffffu, tm_warp, 0); h.tm_visits = tm_visits;
     unsigned long long ded = 0;
     unsigned rot = fp_rot;
     int it = 0, f;
@@ -1326,6 +1327,11 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   }
   k.sync();
   k.tm_warp = 0; k.tm_visits = 0;
+  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && !P.tmem_cols && threadIdx.x < 32) {
+    // A CTA of a kernel that carries tensor-memory code holds the SM's allocation permit until it gives it up, and no
+    // second CTA starts on the SM meanwhile (measured: TB_TMEM=0 ran one CTA per SM): give it up at once.
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && P.tmem_cols) {
     // the table goes to tensor memory: one warp allocates the CTA's columns, every warp stores the words of its own
     // first tmem_visits visits into its quarter of the lanes (chunk ch = warp + k * nwarps at columns 2k, 2k + 1)
@@ -1850,7 +1856,11 @@ static tb_status set_smem_attr(tb_solver* s) {
                   m, (int)act, s->threads, s->shared_bytes, fa.sharedSizeBytes, fa.numRegs, fa.localSizeBytes, per_sm, s->blocks_per_sm);
       }
       if (per_sm < 1) { set_error("the solve kernel does not fit on an SM with this configuration"); return TB_ERR_UNSUPPORTED; }
-      if (env_int("TB_IGNORE_OCCUPANCY_API", 0)) per_sm = std::max(per_sm, s->blocks_per_sm);
+      // The occupancy API answers "one CTA per SM" for every kernel that contains tcgen05.alloc, whatever it allocates
+      // (measured). The policy above already keeps to 1024 resident threads per SM at 64 registers (__launch_bounds__)
+      // and to the shared memory of the SM, and the CTAs split the 512 tensor-memory columns between them (tb_create):
+      // for those kernels its own arithmetic stands.
+      if ((TB_TMEM_CODE && m == TB_MEM_STORE_SHARED && !act && TBC_U == 1) || env_int("TB_IGNORE_OCCUPANCY_API", 0)) per_sm = std::max(per_sm, s->blocks_per_sm);
       if (per_sm < s->blocks_per_sm) {
         s->blocks_per_sm = per_sm;
         int blocks = per_sm * s->num_sms;
