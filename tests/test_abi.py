@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(abi.TbStrategy) == 24
     assert C.sizeof(abi.TbProblem) == 56
     assert C.sizeof(abi.TbOptions) == 80
-    assert C.sizeof(abi.TbStats) == 32 + 8 * 10 + 8 * 3 + 8 + 8 * abi.NUM_TIMERS + 8 + 8 + 8 + 8
+    assert C.sizeof(abi.TbStats) == 32 + 8 * 10 + 8 * 3 + 8 + 8 * abi.NUM_TIMERS + 8 + 8 + 8 + 8 + 16
 
 
 def test_version_and_device_count():

@@ -242,3 +242,27 @@ def test_headline_instances_against_their_recorded_optima(eng, name):
     from tests.test_oracle_ops import REL
     for p in pb.props:
         assert REL[int(p["op"])](int(g["lb"][p["x"]]), int(g["lb"][p["y"]]), int(g["lb"][p["z"]]))
+
+
+# ---- tail splitting (adaptive EPS): few subproblems, many blocks ------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["pat4", "pat9", "sudoku_opt4"])
+def test_tail_splitting_keeps_status_and_optimum(eng, name, monkeypatch):
+    """Eight subproblems for hundreds of blocks: the blocks without work wait, the busy ones give their subproblem up
+    and enter its 64 children into the pool; the search is still exhaustive and ends on the reference's optimum, and
+    every subproblem is accounted for: solved + skipped + split = 2^d."""
+    monkeypatch.setenv("TB_SPLIT_MIN_NODES", "256")
+    pb, info = golden_io.load(name)
+    with eng.Solver(pb, subproblems_power=3, timeout_ms=60000) as s:
+        g = s.solve()
+    st = g["stats"]
+    assert g["has_solution"] and g["exhaustive"]
+    assert golden_io.user_objective(info, g["lb"], g["ub"]) == info["expected"]
+    assert st["eps_solved_subproblems"] + st["eps_skipped_subproblems"] + st["eps_split_subproblems"] == 8
+    assert st["eps_split_subproblems"] > 0 and st["eps_split_parts_solved"] > 0
+    # and with splitting off the same answer (one block per subproblem does all the work)
+    monkeypatch.setenv("TB_SPLIT_BITS", "0")
+    with eng.Solver(pb, subproblems_power=3, timeout_ms=60000) as s:
+        h = s.solve()
+    assert h["exhaustive"] and golden_io.user_objective(info, h["lb"], h["ub"]) == info["expected"]
+    assert h["stats"]["eps_split_subproblems"] == 0

@@ -73,7 +73,8 @@ class TbStats(C.Structure):
                 ("cumulative_time_block_ns", C.c_int64),
                 ("timers_ns", C.c_int64 * NUM_TIMERS),
                 ("kernel_ms", C.c_double), ("eps_stolen_subproblems", C.c_uint64),
-                ("device_bytes", C.c_uint64), ("fixpoint_in_effect", C.c_int32), ("pad_", C.c_int32)]
+                ("device_bytes", C.c_uint64), ("eps_split_subproblems", C.c_uint64), ("eps_split_parts_solved", C.c_uint64),
+                ("fixpoint_in_effect", C.c_int32), ("pad_", C.c_int32)]
 
     def as_dict(self):
         d = {}

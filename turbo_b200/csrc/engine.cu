@@ -131,8 +131,14 @@ __device__ __forceinline__ unsigned long long tmem_ld64(unsigned taddr) {
 struct Ctl {                       // per-CTA control block in static shared memory
   unsigned long long mbar;
   unsigned long long sel_key[2];   // arg-min key of the variable selection (two cells, used in turn)
-  unsigned long long subproblem_k; // counter value of the subproblem being solved: idx = subproblem_k * world + sub_owner
-  int sub_owner;                   // the rank whose shard it comes from (this GPU's, or a peer's when it was stolen)
+  unsigned long long task_idx;     // the subproblem being solved: dive to index task_idx at depth task_depth
+  int task_depth;                  // P.subproblems_power, or deeper for a child of a subproblem that was split at the tail
+  int task_entry;                  // -1, or the pool entry the child comes from
+  unsigned task_j;                 // its number inside that entry
+  int have_task;                   // next_subproblem() found work
+  unsigned task_nodes;             // nodes spent on this subproblem so far
+  int abandon;                     // the subproblem is being given up (tail splitting)
+  int counted_idle;                // this block is counted among the waiting blocks
   int flags[3];                    // rotating fixpoint flag words
   int sel_first[2];
   int stop, leaf, failed;
@@ -332,29 +338,76 @@ struct Ctx {
       v = old;
     }
   }
-  // G (:873-885) generalised to several GPUs: the next subproblem of this GPU's shard, or, once that is exhausted, of a
-  // peer's shard (work stealing through the peer-mapped dispensers; a CAS, so that a dispenser of another run is never
-  // advanced). Sets c.subproblem_k / c.sub_owner; an exhausted value (idx >= num_subproblems) ends the block.
+  // One child of a split subproblem, if there is an open entry in the pool.
+  __device__ __forceinline__ bool take_split() {
+    if (!P.split_bits) return false;
+    const unsigned n = min(*(volatile unsigned*)(P.split_ctl + TB_SPLIT_N), (unsigned)TB_SPLIT_CAP);
+    unsigned first_open = n;
+    for (unsigned i = *(volatile unsigned*)(P.split_ctl + TB_SPLIT_HINT); i < n; ++i) {
+      SplitEntry* e = P.split_pool + i;
+      const unsigned cnt = *(volatile unsigned*)&e->count;
+      if (cnt == 0) { first_open = min(first_open, i); continue; }            // being written
+      if (*(volatile unsigned*)&e->next >= cnt) continue;
+      first_open = min(first_open, i);
+      const unsigned j = atomicAdd(&e->next, 1u);
+      if (j < cnt) {
+        c.task_idx = e->base + (unsigned long long)j; c.task_depth = e->depth; c.task_entry = (int)i; c.task_j = j;
+        c.have_task = 1;
+        return true;
+      }
+    }
+    if (first_open > *(volatile unsigned*)(P.split_ctl + TB_SPLIT_HINT)) atomicMax(P.split_ctl + TB_SPLIT_HINT, first_open);
+    return false;
+  }
+
+  // The subproblem this block has been working on becomes 2^split_bits children in the pool (thread 0).
+  __device__ __forceinline__ bool push_split() {
+    const unsigned i = atomicAdd(P.split_ctl + TB_SPLIT_N, 1u);
+    if (i >= (unsigned)TB_SPLIT_CAP) return false;
+    SplitEntry* e = P.split_pool + i;
+    e->base = c.task_idx << P.split_bits; e->depth = c.task_depth + P.split_bits; e->next = 0u;
+    __threadfence();
+    *(volatile unsigned*)&e->count = 1u << P.split_bits;
+    st->eps_split += 1;
+    return true;
+  }
+
+  // G (:873-885) generalised: the next subproblem of this GPU's shard; once that is exhausted a child of a subproblem
+  // that was split at the tail, then a subproblem of a peer's shard (work stealing through the peer-mapped dispensers; a
+  // CAS, so that a dispenser of another run is never advanced). With nothing to take the block WAITS (that is what makes
+  // the busy blocks split), until work appears or every block of the grid is waiting or gone. Thread 0.
   __device__ __forceinline__ void next_subproblem() {
     const unsigned long long world = (unsigned long long)P.world;
-    unsigned long long k = atomicAdd(P.cells + TB_CELL_NEXT, 1ull) & TB_K_MASK;
-    int owner = P.rank;
-    if (k * world + (unsigned long long)P.rank >= P.num_subproblems && P.steal) {
+    c.have_task = 0; c.task_entry = -1; c.task_depth = P.subproblems_power;
+    const unsigned long long k = atomicAdd(P.cells + TB_CELL_NEXT, 1ull) & TB_K_MASK;
+    if (k * world + (unsigned long long)P.rank < P.num_subproblems) { c.task_idx = k * world + (unsigned long long)P.rank; c.have_task = 1; return; }
+    if (take_split()) return;
+    if (P.steal) {
       for (int t = 0; t < P.npeers; ++t) {
         const int g = (slot + t) % P.npeers;
         unsigned long long* cell = P.peer_cells[g] + TB_CELL_NEXT;
         unsigned long long v = *(volatile unsigned long long*)cell;
-        bool got = false;
         while ((v >> TB_K_BITS) == (unsigned long long)P.epoch &&
                (v & TB_K_MASK) * world + (unsigned long long)P.peer_rank[g] < P.num_subproblems) {
           const unsigned long long old = atomicCAS_system(cell, v, v + 1ull);
-          if (old == v) { got = true; break; }
+          if (old == v) {
+            c.task_idx = (v & TB_K_MASK) * world + (unsigned long long)P.peer_rank[g]; c.have_task = 1;
+            st->eps_stolen += 1;
+            return;
+          }
           v = old;
         }
-        if (got) { k = v & TB_K_MASK; owner = P.peer_rank[g]; st->eps_stolen += 1; break; }
       }
     }
-    c.subproblem_k = k; c.sub_owner = owner;
+    if (!P.split_bits) return;
+    atomicAdd(P.split_ctl + TB_SPLIT_WAITING, 1u);
+    c.counted_idle = 1;
+    for (;;) {
+      if (stop_raised()) return;
+      if (take_split()) { atomicSub(P.split_ctl + TB_SPLIT_WAITING, 1u); c.counted_idle = 0; return; }
+      if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) + *(volatile unsigned*)(P.split_ctl + TB_SPLIT_GONE) >= (unsigned)nslots) return;
+      __nanosleep(2000);
+    }
   }
 
   // ---- copies between the block store and a global image of it ---------------------------------
@@ -588,7 +641,7 @@ struct Ctx {
   // The words of the chunk a warp visits `tk` visits into its sweep: from tensor memory when they are there.
   __device__ __forceinline__ Words next_words(const Hot& h, Walk3& w) const {
     Words r;
-    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && w.tk < h.tm_visits) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
+    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && __builtin_expect(w.tk < h.tm_visits, 1)) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
     else r = load_words(h.words, w.widx);
     ++w.tk;
     return r;
@@ -611,7 +664,7 @@ struct Ctx {
       for (int u = 0; u < TBC_U; ++u) tbd::load_snap<CLS>(store, fa[u], fb[u], fc[u], s[u]);
 #pragma unroll
       for (int u = 0; u < TBC_U; ++u) work |= tbd::has_work<CLS>(s[u]);
-      if (__any_sync(0xffffffffu, work)) {
+      if (__builtin_expect(__any_sync(0xffffffffu, work), 0)) {
         unsigned n = 0;
         for (;;) {
 #pragma unroll
@@ -1099,12 +1152,13 @@ struct Ctx {
     int mode = M_START;
     for (;;) {
       if (mode == M_START) {
-        idx = c.subproblem_k * world + (unsigned long long)c.sub_owner;     // a shard is idx = owner (mod world)
-        if (idx >= nsub || c.stop) break;
+        if (!c.have_task || c.stop) break;
+        idx = c.task_idx;
         sync();
         if (tid == 0) {
           c.cur_strategy = 0; c.next_unassigned = 0; c.depth = 0;
-          c.remaining_depth = P.subproblems_power; c.leaf = 0; c.failed = 0;
+          c.remaining_depth = c.task_depth; c.leaf = 0; c.failed = 0;
+          c.task_nodes = 0; c.abandon = 0;
           c.t_mark = (long long)globaltimer_ns();
         }
         for (int i = tid; i < P.nsnap; i += T) g_snap_tag[i] = -1;       // snapshots belong to one subproblem
@@ -1119,7 +1173,11 @@ struct Ctx {
         const int remaining = c.remaining_depth;
         if (c.leaf && !c.stop) {
           // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
-          if (tid == 0) {
+          if (tid == 0 && c.task_entry >= 0) {
+            // a child of a split subproblem: its siblings below the same leaf need no dive either
+            SplitEntry* e = P.split_pool + c.task_entry;
+            if (remaining < 31) atomicMax(&e->next, min(e->count, ((c.task_j >> remaining) + 1u) << remaining));
+          } else if (tid == 0) {
             // nobody needs to dive into [idx, next) any more: advance every shard's dispenser past it
             const unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
             dispenser_skip_to(-1, next <= rank ? 0ull : (next - rank + world - 1ull) / world);
@@ -1149,13 +1207,19 @@ struct Ctx {
             }
             if (appx == TBD_NINF) { c.stop = 1; raise_stop(true); }
           }
+          // tail splitting: somebody is waiting for work and this subproblem has been going on for a while
+          if (tid == 0 && P.split_bits && ++c.task_nodes >= (unsigned)P.split_min_nodes && (c.task_nodes & 255u) == 0u &&
+              *(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) > 0u && c.task_depth + P.split_bits <= 56 &&
+              *(volatile unsigned*)(P.split_ctl + TB_SPLIT_N) < (unsigned)TB_SPLIT_CAP)
+            c.abandon = push_split() ? 1 : 0;
           sync();
           if (c.stop) mode = M_SOLVE_END;
+          else if (c.abandon) mode = M_NEXT;          // its children are in the pool now; this block takes one of them
         }
       }
       if (mode == M_SOLVE_END) {
         sync();
-        if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !stop_raised()) st->eps_solved += 1;
+        if (tid == 0 && !(P.cutnodes && st->nodes >= P.cutnodes) && !stop_raised()) { if (c.task_entry < 0) st->eps_solved += 1; else st->eps_parts += 1; }
         mode = M_NEXT;
       }
       if (mode == M_NEXT) {
@@ -1395,13 +1459,17 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
   const int tid = k.tid;
   BlockStats* st = k.st;
   if (tid == 0) {
-    c.subproblem_k = (unsigned long long)k.slot; c.sub_owner = P.rank;
+    c.task_idx = (unsigned long long)k.slot * (unsigned long long)P.world + (unsigned long long)P.rank;
+    c.task_depth = P.subproblems_power; c.task_entry = -1; c.task_j = 0; c.counted_idle = 0; c.abandon = 0; c.task_nodes = 0;
+    c.have_task = c.task_idx < P.num_subproblems;
+    if (!c.have_task) k.next_subproblem();       // more blocks than subproblems: wait for the tail to be split
     // this run's epoch enters the incumbent cell: whatever an earlier run (of this solver or of a peer) left is void
     atomicMin(P.cells + TB_CELL_BOUND, k.bound_word(TBD_PINF));
   }
   k.sync();
   k.search();
   if (tid == 0) {
+    if (P.split_bits && !c.counted_idle) atomicAdd(P.split_ctl + TB_SPLIT_GONE, 1u);      // (waiting blocks stay counted as such)
     if (!(P.cutnodes && st->nodes >= P.cutnodes) && !k.stop_raised()) st->blocks_done = 1;
     st->t_idle = (long long)(globaltimer_ns() - P.t_start);
   }
@@ -1901,6 +1969,12 @@ static tb_status ensure_scratch(tb_solver* s, int slots) {
     }
   }
   if ((rc = dev_alloc(s, &P.stats, (size_t)slots))) return rc;
+  if (!P.split_pool) {
+    if ((rc = dev_alloc(s, &P.split_pool, (size_t)TB_SPLIT_CAP))) return rc;
+    if ((rc = dev_alloc(s, &P.split_ctl, 8))) return rc;
+    P.split_bits = std::max(0, std::min(12, env_int("TB_SPLIT_BITS", 6)));
+    P.split_min_nodes = std::max(256, env_int("TB_SPLIT_MIN_NODES", 4096));
+  }
   s->scratch_blocks = slots;
   return TB_OK;
 }
@@ -2258,6 +2332,7 @@ static void reduce_stats(const std::vector<BlockStats>& bs, tb_stats* st, int* b
     st->exhaustive = st->exhaustive && b.exhaustive;
     st->eps_solved_subproblems += b.eps_solved; st->eps_skipped_subproblems += b.eps_skipped;
     st->eps_stolen_subproblems += b.eps_stolen;
+    st->eps_split_subproblems += b.eps_split; st->eps_split_parts_solved += b.eps_parts;
     st->num_blocks_done += b.blocks_done;
     st->fixpoint_iterations += b.fixpoint_iterations; st->num_deductions += b.deductions;
     st->bounds_narrowed += b.narrowed;
@@ -2330,6 +2405,10 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
     CU(cudaMemsetAsync(s->P.stream_lock, 0, sizeof(int) * TB_STREAM_MAX_SLOTS, s->stream));
     memset(s->h_stream_rec, 0, sizeof(StreamRec) * (size_t)P.stream_slots);
     s->stream_read = 0;
+  }
+  if (P.split_bits) {
+    CU(cudaMemsetAsync(P.split_ctl, 0, 8 * sizeof(unsigned), s->stream));
+    CU(cudaMemsetAsync(P.split_pool, 0, sizeof(SplitEntry) * (size_t)TB_SPLIT_CAP, s->stream));
   }
   CU(cudaMemcpyAsync(s->d_cells + TB_CELL_NEXT, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
@@ -2441,6 +2520,7 @@ extern "C" tb_status tb_result_reduce(const void* bufs, int32_t n, size_t stride
     t.exhaustive = t.exhaustive && s.exhaustive && h.exhaustive;
     t.eps_solved_subproblems += s.eps_solved_subproblems; t.eps_skipped_subproblems += s.eps_skipped_subproblems;
     t.eps_stolen_subproblems += s.eps_stolen_subproblems;
+    t.eps_split_subproblems += s.eps_split_subproblems; t.eps_split_parts_solved += s.eps_split_parts_solved;
     t.num_blocks_done += s.num_blocks_done;
     t.fixpoint_iterations += s.fixpoint_iterations; t.num_deductions += s.num_deductions; t.bounds_narrowed += s.bounds_narrowed;
     t.cumulative_time_block_ns += s.cumulative_time_block_ns;

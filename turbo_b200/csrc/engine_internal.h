@@ -20,6 +20,7 @@ struct DevStrategy {            // StrategyType (barebones :84)
 // Per-block statistics: Statistics<> fields written on the device (include/statistics.hpp:137-154).
 struct BlockStats {
   unsigned long long nodes, fails, solutions, eps_solved, eps_skipped, eps_stolen, blocks_done;
+  unsigned long long eps_split, eps_parts;     // subproblems given up and re-split at the tail / parts of them solved
   unsigned long long fixpoint_iterations, deductions, narrowed;
   long long t_fixpoint, t_dive, t_best, t_idle;
   int depth_max, exhaustive, best_bound, has_best, error, pad_;
@@ -48,6 +49,21 @@ struct StreamRec {
   long long t_ns;
 };
 #define TB_STREAM_MAX_SLOTS 64
+
+// Tail splitting (adaptive EPS). The reference fixes 2^d subproblems up front (barebones :548-555); the last, hard ones
+// then keep one block each busy while every other block has nothing left to do. Here a block that has worked on one
+// subproblem for split_min_nodes nodes while other blocks WAIT gives the subproblem up and enters its 2^split_bits
+// children (the subproblems idx * 2^e + j of depth d + e: a dive is a pure function of (root, index, depth)) into a
+// pool the waiting blocks - and the block itself - take their work from. Entries can be split again.
+struct SplitEntry {
+  unsigned long long base;      // index of the first child at depth `depth`
+  int depth;                    // dive depth of the children
+  unsigned count;               // number of children (0 = entry not published yet)
+  unsigned next;                // dispenser over the children (fetch-add; monotone max on a failed subtree)
+  unsigned pad_[3];
+};
+#define TB_SPLIT_CAP 16384
+enum { TB_SPLIT_N = 0, TB_SPLIT_WAITING = 1, TB_SPLIT_GONE = 2, TB_SPLIT_HINT = 3 };   // words of DevParams::split_ctl
 
 // Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
 // flattened to plain device pointers (no managed memory, no device-side malloc).
@@ -90,6 +106,10 @@ struct DevParams {
   const int* watch_off;                  // vpad + 1 offsets into watch_list
   const int* watch_list;                 // chunk ids, ascending per slot
   const unsigned long long* watch_inline; // per slot: its first three watchers as 16-bit chunk ids (0xFFFF = none), top 16 bits 0xFFFE = more in the CSR list
+  // tail splitting (see SplitEntry)
+  SplitEntry* split_pool;                // [TB_SPLIT_CAP]
+  unsigned* split_ctl;                   // entries appended / blocks waiting for work / blocks gone / lowest open entry
+  int split_bits, split_min_nodes;       // e (0 = off) and the node count after which a subproblem may be given up
   // intermediate solutions (tb_stream_solutions): ring of store images in device memory + records in mapped host memory
   int* stream_img;                       // [stream_slots] images of 2 * vpad ints
   StreamRec* stream_rec;                 // [stream_slots], pinned host memory

@@ -251,6 +251,7 @@ void print_solver_stats(const Stat& S, const tb_stats& st, int verbose, size_t v
   S.u("eps_solved_subproblems", st.eps_solved_subproblems);
   S.u("eps_skipped_subproblems", st.eps_skipped_subproblems);
   if (st.eps_stolen_subproblems) S.u("eps_stolen_subproblems", st.eps_stolen_subproblems);
+  if (st.eps_split_subproblems) { S.u("eps_split_subproblems", st.eps_split_subproblems); S.u("eps_split_parts_solved", st.eps_split_parts_solved); }
   S.u("num_blocks_done", st.num_blocks_done);
   S.u("fixpoint_iterations", st.fixpoint_iterations);
   S.u("num_deductions", st.num_deductions);
