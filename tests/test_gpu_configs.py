@@ -246,7 +246,7 @@ def test_headline_instances_against_their_recorded_optima(eng, name):
 
 # ---- tail splitting (adaptive EPS): few subproblems, many blocks ------------------------------------------------------------
 
-@pytest.mark.parametrize("name", ["pat4", "pat9", "sudoku_opt4"])
+@pytest.mark.parametrize("name", ["pat13", "pat12", "triangular9"])       # the known answers with the largest search trees
 def test_tail_splitting_keeps_status_and_optimum(eng, name, monkeypatch):
     """Eight subproblems for hundreds of blocks: the blocks without work wait, the busy ones give their subproblem up
     and enter its 64 children into the pool; the search is still exhaustive and ends on the reference's optimum, and

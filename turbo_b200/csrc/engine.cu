@@ -2720,9 +2720,22 @@ extern "C" tb_status tb_import_peer_bounds(tb_solver* s, const void* handles64, 
   for (int i = 0; i < npeers; ++i) {
     cudaIpcMemHandle_t h;
     memcpy(&h, (const char*)handles64 + (size_t)i * 64, 64);
+    // A peer's cell block is recycled by its solvers (acquire_cells), so the same handle comes back with every solver of
+    // a create / solve / destroy cycle: the mapping is opened once per process and kept (cudaIpcCloseMemHandle alone
+    // took 80 ms of every tb_destroy; profiles/r02_multi_gpu_bench_n2.json).
     void* p = nullptr;
-    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    s->ipc_opened.push_back(p);
+    {
+      static std::mutex m;
+      static std::vector<std::pair<std::string, void*>> opened[64];
+      std::lock_guard<std::mutex> lock(m);
+      const std::string key((const char*)&h, 64);
+      auto& tab = opened[s->device >= 0 && s->device < 64 ? s->device : 0];
+      for (auto& kv : tab) if (kv.first == key) { p = kv.second; break; }
+      if (!p) {
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        tab.emplace_back(key, p);
+      }
+    }
     s->peer_cells.push_back((unsigned long long*)p);
     // handles come in rank order with this solver's own rank left out
     s->peer_ranks.push_back(i < s->opt.gpu_rank ? i : i + 1);
