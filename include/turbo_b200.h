@@ -225,6 +225,10 @@ typedef struct {
 } tb_layout_info;
 tb_status tb_layout_describe(const tb_problem* problem, int32_t nbanks, tb_layout_info* info, int32_t* slot_of);
 const char* tb_layout_class_name(int32_t cls);
+/* STORE_CLUSTER placement (host only): the share of the operand loads of one sweep that stay in the CTA whose warps
+ * evaluate the propagator, with the layout pass's placement (variables that occur together share a CTA, a CTA gets
+ * the chunks whose operands mostly live in it) and with plain striping (slot = variable index). */
+tb_status tb_layout_cluster_locality(const tb_problem* problem, int32_t cluster, int32_t warps_per_cta, double* placed, double* striped);
 /* Watch lists of the active-set fixpoint: for every slot of the store image the chunks (32 propagators of the device
  * table) that load it, as CSR (off has *nslots + 1 entries, list *nentries); chunk_of_prop[i] = chunk of propagator i.
  * Call with NULL buffers first to get the sizes. */

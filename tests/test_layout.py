@@ -94,3 +94,20 @@ def test_watch_lists_cover_every_loaded_operand(name):
             if not fixed[v] and ch not in watch[int(slot_of[v])]:
                 missing += 1
     assert missing == 0
+
+
+def test_cluster_placement_keeps_most_operand_loads_in_the_evaluating_cta():
+    """STORE_CLUSTER: variables that occur together share a CTA and a CTA evaluates the chunks whose operands mostly
+    live in it; only the cut goes through DSMEM. Striping (slot = variable index) keeps 1 / C of the loads local."""
+    import ctypes as C
+    from tests import golden_io
+    L = engine.lib()
+    L.tb_layout_cluster_locality.argtypes = [C.POINTER(abi.TbProblem), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tb_layout_cluster_locality.restype = C.c_int
+    pb, _ = golden_io.load("example_wordpress7_500")
+    placed, striped = C.c_double(0), C.c_double(0)
+    assert L.tb_layout_cluster_locality(C.byref(pb.c), 4, 32, C.byref(placed), C.byref(striped)) == 0
+    assert 0.2 < striped.value < 0.3 and placed.value > 0.65
+    rnd = tnf_gen.planted(4000, 12000, 3)            # a random network has no locality beyond "two operands of three"
+    assert L.tb_layout_cluster_locality(C.byref(rnd.c), 4, 32, C.byref(placed), C.byref(striped)) == 0
+    assert placed.value > striped.value + 0.1 and striped.value < 0.3

@@ -2057,9 +2057,13 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     const bool shared_store = s->mem_kind == TB_MEM_STORE_SHARED || s->mem_kind == TB_MEM_TCN_SHARED;
     lo.nbanks = shared_store && env_int("TB_NO_BANK_LAYOUT", 0) == 0 ? 16 : 0;
     lo.slot_align = shared_store ? 32 : (s->mem_kind == TB_MEM_STORE_CLUSTER ? 4 * s->cluster : 4);
+    if (s->mem_kind == TB_MEM_STORE_CLUSTER && env_int("TB_CLUSTER_LOCALITY", 1) != 0) { lo.cluster = s->cluster; lo.cluster_warps = s->threads / 32; }
     std::string err;
     if ((rc = tb_build_layout(pb, lo, &s->layout, &err)) != TB_OK) { set_error(err); return fail(rc); }
     const TnfLayout& L = s->layout;
+    if (s->mem_kind == TB_MEM_STORE_CLUSTER && getenv("TB_TRACE_TIMING"))
+      fprintf(stderr, "[tb config] store_cluster x%d: %.1f %% of the operand loads of a sweep stay in the evaluating CTA (striped placement: %.1f %%)\n",
+              s->cluster, 100.0 * L.cluster_local_fraction, 100.0 / s->cluster);
     P.vpad = L.nslots;
     if (s->mem_kind == TB_MEM_STORE_CLUSTER && P.vpad != P.vc * s->cluster) { set_error("internal: cluster slice size mismatch"); return fail(TB_ERR_INVALID); }
     s->store_bytes = (size_t)P.vpad * 8;

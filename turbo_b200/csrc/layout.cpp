@@ -88,6 +88,115 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cls < items[b].cls; });
 
+  // ---- STORE_CLUSTER: which CTA a variable lives in ------------------------------------------------------------
+  // part[v] in 0..C-1, every part at most nslots / C variables. Breadth-first order over the propagator hypergraph
+  // (variables that occur together are visited together), cut into C consecutive runs.
+  const int C = opt.cluster > 1 ? opt.cluster : 0;
+  std::vector<int> part;
+  if (C) {
+    const int cap = L.nslots / C;
+    part.assign((size_t)V, -1);
+    // variable -> propagators (CSR), loaded operands only
+    std::vector<int> deg((size_t)V, 0);
+    auto each_operand = [&](const Item& it, auto&& f) { if (loads_x(it.cls)) f(it.x); f(it.y); if (loads_z(it.cls)) f(it.z); };
+    for (const Item& it : items) each_operand(it, [&](int v) { ++deg[v]; });
+    std::vector<size_t> off((size_t)V + 1, 0);
+    for (int v = 0; v < V; ++v) off[v + 1] = off[v] + (size_t)deg[v];
+    std::vector<int> inc(off[V]);
+    {
+      std::vector<size_t> fill(off.begin(), off.end() - 1);
+      for (int i = 0; i < P; ++i) each_operand(items[(size_t)i], [&](int v) { inc[fill[v]++] = i; });
+    }
+    std::vector<int> bfs;
+    bfs.reserve((size_t)V);
+    std::vector<char> seen((size_t)V, 0), pseen((size_t)P, 0);
+    for (int root = 0; root < V; ++root) {
+      if (seen[root] || !deg[root]) continue;
+      size_t head = bfs.size();
+      bfs.push_back(root); seen[root] = 1;
+      while (head < bfs.size()) {
+        const int v = bfs[head++];
+        for (size_t k = off[v]; k < off[v + 1]; ++k) {
+          const int i = inc[k];
+          if (pseen[i]) continue;
+          pseen[i] = 1;
+          each_operand(items[(size_t)i], [&](int u) { if (!seen[u]) { seen[u] = 1; bfs.push_back(u); } });
+        }
+      }
+    }
+    for (int v = 0; v < V; ++v) if (!seen[v]) bfs.push_back(v);       // variables no propagator loads
+    for (size_t k = 0; k < bfs.size(); ++k) part[(size_t)bfs[k]] = std::min(C - 1, (int)(k / (size_t)cap));
+    // Refinement: label propagation under the capacity. A variable wants the part most of its co-operands live in;
+    // wishes a -> b are granted in pairs with wishes b -> a (largest gains first), so every part keeps its size.
+    {
+      std::vector<int> want((size_t)V), gain((size_t)V);
+      for (int pass = 0; pass < 12; ++pass) {
+        for (int v = 0; v < V; ++v) {
+          want[(size_t)v] = part[(size_t)v]; gain[(size_t)v] = 0;
+          if (!deg[v] || deg[v] > 4096) continue;            // (hubs stay where they are: everybody's neighbour)
+          int cnt[16] = {0};
+          for (size_t k = off[v]; k < off[v + 1]; ++k)
+            each_operand(items[(size_t)inc[k]], [&](int u) { if (u != v) ++cnt[part[(size_t)u] & 15]; });
+          int best = part[(size_t)v];
+          for (int q = 0; q < C; ++q) if (cnt[q] > cnt[best]) best = q;
+          want[(size_t)v] = best; gain[(size_t)v] = cnt[best] - cnt[part[(size_t)v]];
+        }
+        std::vector<std::vector<int>> wish((size_t)C * C);
+        for (int v = 0; v < V; ++v) if (want[(size_t)v] != part[(size_t)v]) wish[(size_t)part[(size_t)v] * C + want[(size_t)v]].push_back(v);
+        size_t moved = 0;
+        for (int p = 0; p < C; ++p)
+          for (int q = p + 1; q < C; ++q) {
+            auto& ab = wish[(size_t)p * C + q];
+            auto& ba = wish[(size_t)q * C + p];
+            auto by_gain = [&](int x, int y) { return gain[(size_t)x] > gain[(size_t)y]; };
+            std::stable_sort(ab.begin(), ab.end(), by_gain);
+            std::stable_sort(ba.begin(), ba.end(), by_gain);
+            const size_t n = std::min(ab.size(), ba.size());
+            for (size_t k = 0; k < n; ++k) { part[(size_t)ab[k]] = q; part[(size_t)ba[k]] = p; }
+            moved += 2 * n;
+          }
+        if (moved * 200 < (size_t)V) break;                  // under half a percent moved: settled
+      }
+    }
+    // ---- and which CTA a propagator is evaluated in: the one most of its operands live in. Inside a class the chunks
+    // are filled so that the chunk a CTA's warps visit (ch mod (C * warps) / warps) holds that CTA's propagators.
+    const int W = std::max(1, opt.cluster_warps);
+    auto home = [&](const Item& it) {
+      int cnt[16] = {0};
+      each_operand(it, [&](int v) { ++cnt[part[v] & 15]; });
+      int best = part[it.y];
+      for (int q = 0; q < C; ++q) if (cnt[q] > cnt[best]) best = q;
+      return best;
+    };
+    std::vector<int> reordered;
+    reordered.reserve(order.size());
+    size_t i = 0, chunk = 0;
+    const size_t CHK = (size_t)32 * TBC_U;
+    while (i < order.size()) {
+      const int c = items[(size_t)order[i]].cls;
+      std::vector<std::vector<int>> bucket((size_t)C);
+      size_t n = 0;
+      for (; i < order.size() && items[(size_t)order[i]].cls == c; ++i, ++n) bucket[(size_t)home(items[(size_t)order[i]])].push_back(order[i]);
+      std::vector<size_t> taken((size_t)C, 0);
+      size_t left = n;
+      while (left) {
+        const int cta = (int)((chunk % ((size_t)C * W)) / (size_t)W);
+        size_t want = std::min(CHK, left);
+        int q = cta;
+        while (want) {
+          if (taken[(size_t)q] == bucket[(size_t)q].size()) {          // this CTA's propagators are used up: take from the fullest bucket
+            q = 0;
+            for (int r = 1; r < C; ++r) if (bucket[(size_t)r].size() - taken[(size_t)r] > bucket[(size_t)q].size() - taken[(size_t)q]) q = r;
+          }
+          reordered.push_back(bucket[(size_t)q][taken[(size_t)q]++]);
+          --want; --left;
+        }
+        ++chunk;
+      }
+    }
+    order.swap(reordered);
+  }
+
   // row table: rows of 32 lanes holding indices into `items`, -1 = padding (filled with a copy of the class's
   // last propagator). A chunk is TBC_U consecutive rows of one class: lane l of a warp evaluates lane l of each.
   const int CH = 32 * TBC_U;
@@ -137,6 +246,27 @@ tb_status tb_build_layout(const tb_problem* pb, const TnfLayoutOptions& opt, Tnf
         sets.push_back(std::move(vs));
       }
     }
+  }
+  if (C) {
+    // slot = local index * C + CTA (the device finds slot s in CTA s mod C)
+    std::vector<int> next((size_t)C);
+    std::iota(next.begin(), next.end(), 0);
+    for (int v = 0; v < V; ++v) { L.slot_of[v] = next[(size_t)part[v]]; next[(size_t)part[v]] += C; }
+    L.identity = true;
+    for (int v = 0; v < V; ++v) if (L.slot_of[v] != v) { L.identity = false; break; }
+    // how local the sweep is: operand loads that stay in the CTA whose warps visit the chunk
+    const int W = std::max(1, opt.cluster_warps);
+    unsigned long long local = 0, total = 0;
+    for (size_t k = 0; k < lanes.size(); ++k) {
+      if (lanes[k] < 0) continue;
+      const Item& it = items[(size_t)lanes[k]];
+      const int cta = (int)(((k / 32 / TBC_U) % ((size_t)C * W)) / (size_t)W);
+      auto f = [&](int v) { ++total; local += (L.slot_of[v] % C) == cta; };
+      if (loads_x(it.cls)) f(it.x);
+      f(it.y);
+      if (loads_z(it.cls)) f(it.z);
+    }
+    L.cluster_local_fraction = total ? (double)local / (double)total : 0.0;
   }
   if (opt.nbanks > 0 && V > 0) {
     const int NB = opt.nbanks;
@@ -299,6 +429,44 @@ extern "C" tb_status tb_layout_describe(const tb_problem* pb, int32_t nbanks, tb
   info->loads_per_sweep = L.loads_per_sweep;
   info->wavefronts_per_load = L.wavefronts_per_load;
   if (slot_of) std::copy(L.slot_of.begin(), L.slot_of.end(), slot_of);
+  return TB_OK;
+}
+
+extern "C" tb_status tb_layout_cluster_locality(const tb_problem* pb, int32_t cluster, int32_t warps_per_cta, double* placed, double* striped) {
+  if (!pb || cluster < 2 || cluster > 16 || warps_per_cta < 1) return TB_ERR_INVALID;
+  std::string err;
+  for (int pass = 0; pass < 2; ++pass) {
+    TnfLayoutOptions lo;
+    lo.slot_align = 4 * cluster;
+    TnfLayout L;
+    double frac = 0.0;
+    if (pass == 0) {
+      lo.cluster = cluster; lo.cluster_warps = warps_per_cta;
+      tb_status rc = tb_build_layout(pb, lo, &L, &err);
+      if (rc != TB_OK) return rc;
+      frac = L.cluster_local_fraction;
+      if (placed) *placed = frac;
+    } else {
+      // the striped placement (slot = variable index, slot s in CTA s mod C, chunks in the ternariser's order)
+      tb_status rc = tb_build_layout(pb, lo, &L, &err);
+      if (rc != TB_OK) return rc;
+      unsigned long long local = 0, total = 0;
+      const size_t period = (size_t)cluster * (size_t)warps_per_cta;
+      for (int i = 0; i < pb->nprops; ++i) {
+        const int ch = L.chunk_of_prop[(size_t)i];
+        if (ch < 0) continue;
+        const int cta = (int)(((size_t)ch % period) / (size_t)warps_per_cta);
+        bool sw = false;
+        const int cls = tb_classify(pb->props[i], pb->lb, pb->ub, &sw);
+        const int y = sw ? pb->props[i].z : pb->props[i].y, z = sw ? pb->props[i].y : pb->props[i].z;
+        auto f = [&](int v) { ++total; local += (L.slot_of[(size_t)v] % cluster) == cta; };
+        if (loads_x(cls)) f(pb->props[i].x);
+        f(y);
+        if (loads_z(cls)) f(z);
+      }
+      if (striped) *striped = total ? (double)local / (double)total : 0.0;
+    }
+  }
   return TB_OK;
 }
 

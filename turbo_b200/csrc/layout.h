@@ -27,6 +27,7 @@ struct TnfLayout {
   bool identity = true;                    // slot_of[v] == v
   std::vector<int> watch_off, watch_list;  // slot -> chunks that load it (CSR over nslots; active-set fixpoint)
   std::vector<int> chunk_of_prop;          // propagator -> chunk of the device table
+  double cluster_local_fraction = 0.0;     // STORE_CLUSTER: share of the operand loads of a sweep that stay in the evaluating CTA
   std::vector<uint64_t> watch_inline;      // per slot: first three watchers as 16-bit ids (0xFFFF = none), top 16 bits 0xFFFE = more in the list
 };
 
@@ -34,6 +35,11 @@ struct TnfLayoutOptions {
   int nbanks = 0;        // 0: keep the caller's variable numbering; 16: the 8-byte banks of one SM
   int lanes_per_set = 16; // lanes whose loads are served together (a half-warp for 8-byte {lb, ub} pairs)
   int slot_align = 4;    // nslots is rounded up to a multiple of this (and of nbanks)
+  // STORE_CLUSTER: the store is striped over `cluster` CTAs (slot s lives in CTA s mod cluster) of `cluster_warps` warps
+  // each, and chunk ch is evaluated by the cluster's warp ch mod (cluster * cluster_warps). With cluster > 1 the pass
+  // places variables that occur together in the same CTA (breadth-first order over the propagators, cut into `cluster`
+  // parts) and gives every CTA the chunks whose operands mostly live in it: only the cut goes through DSMEM.
+  int cluster = 0, cluster_warps = 0;
 };
 
 // Returns TB_OK or TB_ERR_UNSUPPORTED (too many variables for a 21-bit field) with *err set.
