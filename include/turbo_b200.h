@@ -116,7 +116,8 @@ typedef struct {
   double kernel_ms;               /* device time of the solve kernel (CUDA events on its stream) */
   uint64_t eps_stolen_subproblems; /* subproblems this GPU took from a peer's shard once its own was exhausted */
   uint64_t device_bytes;          /* device memory the solver holds (the reference's heap_memory, barebones :579) */
-  uint64_t eps_split_subproblems; /* subproblems given up at the tail of the search and re-split into 2^TB_SPLIT_BITS children */
+  uint64_t eps_split_subproblems; /* subproblems given up at the tail of the search and re-split into 2^TB_SPLIT_BITS children
+                                     (children can be split again; those are not counted) */
   uint64_t eps_split_parts_solved; /* children of those solved; solved + skipped + split = eps_num_subproblems when exhaustive */
   int32_t fixpoint_in_effect;     /* tb_fixpoint_kind the kernels run (an _ACTIVE request falls back to the plain kind on small
                                      tables and outside the shared-memory placements) */

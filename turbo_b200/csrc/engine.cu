@@ -368,7 +368,7 @@ struct Ctx {
     e->base = c.task_idx << P.split_bits; e->depth = c.task_depth + P.split_bits; e->next = 0u;
     __threadfence();
     *(volatile unsigned*)&e->count = 1u << P.split_bits;
-    st->eps_split += 1;
+    if (c.task_entry < 0) st->eps_split += 1;      // (a child that is split again is counted with neither)
     return true;
   }
 
@@ -506,9 +506,14 @@ struct Ctx {
   }
 
   // Orders this thread's published bounds before its re-reads (see tbd::emptied).
+  // (Promptness, not correctness: a re-read that misses the thread's own update finds "work" again and republishes the
+  // same bounds; an empty interval is found by the next evaluation that loads it; the sweep barrier publishes everything.
+  // TB_NO_PUBLISH_FENCE drops it - with a cluster the fence is MEMBAR + ERRBAR + CCTL.IVALL, 12 % of the stall samples.)
   __device__ __forceinline__ void publish_fence() const {
+#ifndef TB_NO_PUBLISH_FENCE
     if (MEM == TB_MEM_STORE_CLUSTER) asm volatile("fence.sc.cluster;" ::: "memory");
     else asm volatile("fence.sc.cta;" ::: "memory");
+#endif
   }
 
   // The part of one sweep that falls in class CLS. A warp walks the whole table ch = warp, warp + nwarps, ...
@@ -781,9 +786,27 @@ struct Ctx {
     if (ACT) atomicOr(act_vbits() + (slot >> 5), 1u << (slot & 31));
   }
 
+  // The chunks that load `slot` are due (direct marking: the publisher does it itself, into the flags of the NEXT sweep).
+  __device__ __forceinline__ void mark_watchers(int slot, unsigned char* dnext, int nwarps, int lw, int FPW) const {
+    const unsigned long long wd = __ldg(P.watch_inline + slot);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned id = (unsigned)(wd >> (16 * k)) & 0xFFFFu;
+      if (id != 0xFFFFu) dnext[(id & (unsigned)(nwarps - 1)) * FPW + (id >> lw)] = 1;
+    }
+    if ((unsigned)(wd >> 48) == 0xFFFEu) {
+      const int e = __ldg(P.watch_off + slot + 1);
+      for (int k = __ldg(P.watch_off + slot) + 3; k < e; ++k) {
+        const int ch = __ldg(P.watch_list + k);
+        dnext[(ch & (nwarps - 1)) * FPW + (ch >> lw)] = 1;
+      }
+    }
+  }
+
   template <int CLS>
   __device__ __forceinline__ void active_visit(Hot& h, const Words& cur, const bool wac1, const int ch, unsigned* vbits,
-                                               unsigned char* ne_slot, unsigned& evals, unsigned& pad_evals, int& late_chg, int& failed) {
+                                               unsigned char* ne_slot, unsigned& evals, unsigned& pad_evals, int& late_chg, int& failed,
+                                               unsigned char* dnext = nullptr, int nwarps = 0, int lw = 0, int FPW = 0) {
     const StoreRef<MEM>& store = h.store;
     int fa[TBC_U], fb[TBC_U], fc[TBC_U];
 #pragma unroll
@@ -804,9 +827,15 @@ struct Ctx {
         tbd::Snap n;
         tbd::narrow<CLS>(s[u], n);
         tbd::publish<CLS>(store, fa[u], fb[u], fc[u], s[u], n, h.narrowed);
-        if (tbd::cls_loads_x(CLS) && ((n.xl != s[u].xl) | (n.xu != s[u].xu))) atomicOr(vbits + (fa[u] >> 5), 1u << (fa[u] & 31));
-        if ((n.yl != s[u].yl) | (n.yu != s[u].yu)) atomicOr(vbits + (fb[u] >> 5), 1u << (fb[u] & 31));
-        if (tbd::cls_loads_z(CLS) && ((n.zl != s[u].zl) | (n.zu != s[u].zu))) atomicOr(vbits + (fc[u] >> 5), 1u << (fc[u] & 31));
+        if (dnext) {
+          if (tbd::cls_loads_x(CLS) && ((n.xl != s[u].xl) | (n.xu != s[u].xu))) mark_watchers(fa[u], dnext, nwarps, lw, FPW);
+          if ((n.yl != s[u].yl) | (n.yu != s[u].yu)) mark_watchers(fb[u], dnext, nwarps, lw, FPW);
+          if (tbd::cls_loads_z(CLS) && ((n.zl != s[u].zl) | (n.zu != s[u].zu))) mark_watchers(fc[u], dnext, nwarps, lw, FPW);
+        } else {
+          if (tbd::cls_loads_x(CLS) && ((n.xl != s[u].xl) | (n.xu != s[u].xu))) atomicOr(vbits + (fa[u] >> 5), 1u << (fa[u] & 31));
+          if ((n.yl != s[u].yl) | (n.yu != s[u].yu)) atomicOr(vbits + (fb[u] >> 5), 1u << (fb[u] & 31));
+          if (tbd::cls_loads_z(CLS) && ((n.zl != s[u].zl) | (n.zu != s[u].zu))) atomicOr(vbits + (fc[u] >> 5), 1u << (fc[u] & 31));
+        }
       }
       bool fail = false;
 #pragma unroll
@@ -832,13 +861,29 @@ struct Ctx {
     unsigned char* dirty = (unsigned char*)(vbits + nvw);
     unsigned char* mydirty = dirty + warp * FPW;
     unsigned char* mynotent = dirty + nwarps * FPW + warp * FPW;
+    // TB_ACTIVE_DIRECT: whoever publishes a bound marks its watchers itself, into a SECOND set of dirty flags that the
+    // next sweep reads: one barrier per sweep instead of two (the marking phase only runs once, at the start of the call,
+    // for what moved outside the fixpoint: the decision, the incumbent, a restored store), and the flag words rotate
+    // across calls as in fixpoint3.
+#ifdef TB_ACTIVE_DIRECT
+    constexpr bool DIRECT = true;
+#else
+    constexpr bool DIRECT = false;
+#endif
+    unsigned char* dirty1 = dirty + 2 * nwarps * FPW;
+    int par = 0;
+    unsigned rot = fp_rot;
     Hot h;
     h.store = store; h.words = words; h.narrowed = narrowed;
+    h.tm = __shfl_sync(0xffffffffu, tm_warp, 0); h.tm_visits = tm_visits;
     unsigned long long ded = 0;
     int it = 0, f;
     for (;; ++it) {
       // ---- marking phase: moved slots -> dirty chunks
-      if (c.dirty_all) {
+      if (DIRECT && it == 0) for (int i = tid; i < nwarps * FPW / 4; i += T) ((unsigned*)dirty1)[i] = 0u;
+      if (DIRECT && it > 0) {
+        // (the publishers of the previous sweep have marked this sweep's chunks already)
+      } else if (c.dirty_all) {
         for (int i = tid; i < nwarps * FPW; i += T) { const int w = i / FPW, k = i - w * FPW; dirty[i] = (k * nwarps + w) < P.nchunks ? 1 : 0; }
         for (int i = tid; i < nvw; i += T) vbits[i] = 0;
       } else {
@@ -869,25 +914,34 @@ struct Ctx {
           }
         }
       }
-      sync();
-      if (tid == 0) { c.dirty_all = 0; c.flags[(it + 1) % 3] = 0; }
+      if (!DIRECT || it == 0) sync();
+      if (tid == 0) {
+        c.dirty_all = 0;
+        if (DIRECT) c.flags[(rot + 1u) % 3u] = 0; else c.flags[(it + 1) % 3] = 0;
+      }
       // ---- sweep: this warp's dirty chunks
       unsigned evals = 0, pad_evals = 0, visits = 0;
       int late_chg = 0, failed = 0;
+      unsigned char* const dcur = (DIRECT && par ? dirty1 : dirty) + warp * FPW;
+      unsigned char* const dnext = DIRECT ? (par ? dirty : dirty1) : nullptr;
       for (int g = 0; g < FPW && !failed; g += 32) {
-        unsigned mask = __ballot_sync(0xffffffffu, mydirty[g + lane] != 0);
-        if (mask) mydirty[g + lane] = 0;
+        unsigned mask = __ballot_sync(0xffffffffu, dcur[g + lane] != 0);
+        if (mask) dcur[g + lane] = 0;
         while (mask && !failed) {
           const int k = g + __ffs((int)mask) - 1;
           mask &= mask - 1;
           const int ch = k * nwarps + warp;
-          const Words cur = load_words(h.words, (ch * 32 + lane) * TBC_U);
+          Words cur;
+          // (the k-th chunk of this warp: its words are in tensor memory when the table fits, a dozen cycles away
+          // instead of an L2 round trip on the critical path of a sweep that visits one or two chunks)
+          if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && k < h.tm_visits) cur.w[0] = tmem_ld64(h.tm + 2u * (unsigned)k);
+          else cur = load_words(h.words, (ch * 32 + lane) * TBC_U);
           int cls = 0;                                          // warp-uniform; the table is sorted by class:
 #pragma unroll
           for (int step = 16; step > 0; step >>= 1)            // largest cls with cls_begin[cls] <= ch (empty classes skipped by <=)
             if (cls + step < TBC_NUM && ch >= P.cls_begin[cls + step]) cls += step;
           switch (cls) {
-#define TB_CASE(CLS) case CLS: active_visit<CLS>(h, cur, wac1, ch, vbits, mynotent + k, evals, pad_evals, late_chg, failed); break;
+#define TB_CASE(CLS) case CLS: active_visit<CLS>(h, cur, wac1, ch, vbits, mynotent + k, evals, pad_evals, late_chg, failed, dnext, nwarps, lw, FPW); break;
             TB_CASE(TBC_ADD_S) TB_CASE(TBC_ADD_XK) TB_CASE(TBC_ADD_ZK) TB_CASE(TBC_ADD_G)
             TB_CASE(TBC_MUL) TB_CASE(TBC_TDIV) TB_CASE(TBC_TMOD) TB_CASE(TBC_MIN) TB_CASE(TBC_MAX)
             TB_CASE(TBC_EQ_S) TB_CASE(TBC_EQ_T) TB_CASE(TBC_EQ_F) TB_CASE(TBC_EQ_ZK) TB_CASE(TBC_EQ_G)
@@ -905,15 +959,17 @@ struct Ctx {
       const bool changed = evals > visits || late_chg;
       int bits = (changed ? F_CHANGED : 0) | (failed ? F_FAILED : 0) | (ne ? F_NOT_ENTAILED : 0);
       bits = __reduce_or_sync(0xffffffffu, bits);
-      const int slot = it % 3;
+      const int slot = DIRECT ? (int)(rot % 3u) : it % 3;
       if (lane == 0 && bits) atomicOr(&c.flags[slot], bits);
       sync();
       f = c.flags[slot];
+      ++rot; par ^= 1;
       if (!(f & F_CHANGED) || (f & F_FAILED)) break;
     }
     iters = it + 1;
     narrowed = h.narrowed;
     deductions += ded;
+    if (DIRECT) { fp_rot = rot; return f; }
     sync();
     if (tid < 3) c.flags[tid] = 0;
     sync();
@@ -1385,18 +1441,18 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   }
   if (ACT) {
     // vbits, dirty and notent flags start clear; the first fixpoint evaluates everything (dirty_all)
-    const int words_ = (P.vpad >> 5) + ((2 * (int)(blockDim.x >> 5) * P.act_fpw + 3) >> 2);
+    const int words_ = (P.vpad >> 5) + ((3 * (int)(blockDim.x >> 5) * P.act_fpw + 3) >> 2);
     unsigned* a = (unsigned*)(dyn + P.act_off);
     for (int i = threadIdx.x; i < words_; i += blockDim.x) a[i] = 0u;
   }
   k.sync();
   k.tm_warp = 0; k.tm_visits = 0;
-  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && !P.tmem_cols && threadIdx.x < 32) {
+  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && TBC_U == 1 && !P.tmem_cols && threadIdx.x < 32) {
     // A CTA of a kernel that carries tensor-memory code holds the SM's allocation permit until it gives it up, and no
     // second CTA starts on the SM meanwhile (measured: TB_TMEM=0 ran one CTA per SM): give it up at once.
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && P.tmem_cols) {
+  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && TBC_U == 1 && P.tmem_cols) {
     // the table goes to tensor memory: one warp allocates the CTA's columns, every warp stores the words of its own
     // first tmem_visits visits into its quarter of the lanes (chunk ch = warp + k * nwarps at columns 2k, 2k + 1)
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31), nwarps = (int)(blockDim.x >> 5);
@@ -1440,7 +1496,7 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
   }
   if (threadIdx.x == 0) bulk_wait_all();     // images still on their way to global memory (best store, snapshots)
   k.sync();        // with a cluster: nobody leaves while a peer may still touch its shared memory
-  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1 && k.P.tmem_cols && threadIdx.x < 32)
+  if (TB_TMEM_CODE && MEM == TB_MEM_STORE_SHARED && TBC_U == 1 && k.P.tmem_cols && threadIdx.x < 32)
     tmem_dealloc(k.lc->tmem_base, (unsigned)k.P.tmem_cols);
 }
 
@@ -1795,7 +1851,7 @@ static tb_status configure(tb_solver* s) {
   const size_t reserved = dp.reservedSharedMemPerBlock + sizeof(Ctl) + 64;
   // the active-set fixpoint keeps one bit per slot and two bytes per chunk next to the store (upper bound here, the
   // exact figure needs the thread count: place_active)
-  const size_t act_b = s->want_active ? (s->store_bytes / 64 + 2 * ((size_t)s->P.nchunks + 1024) + 64) : 0;
+  const size_t act_b = s->want_active ? (s->store_bytes / 64 + 3 * ((size_t)s->P.nchunks + 1024) + 64) : 0;
   const size_t store_b = s->store_bytes + act_b, prop_b = s->prop_bytes;
   auto blocks_for = [&](size_t dyn) -> int {
     if (dyn + sizeof(Ctl) + 64 > max_block_smem) return 0;
@@ -1880,7 +1936,7 @@ static void place_active(tb_solver* s) {
   s->P.act_fpw = std::max(32, (per_warp + 31) / 32 * 32);
   const size_t table = s->mem_kind == TB_MEM_TCN_SHARED ? (size_t)s->P.nchunks * 32 * TBC_U * 8 : 0;
   s->P.act_off = (int)(s->store_bytes + table);
-  const size_t act = (size_t)s->P.vpad / 8 + (size_t)2 * nwarps * s->P.act_fpw;
+  const size_t act = (size_t)s->P.vpad / 8 + (size_t)3 * nwarps * s->P.act_fpw;     // moved bits, dirty, cached ask, second dirty set
   s->shared_bytes = (size_t)s->P.act_off + (act + 15) / 16 * 16;
 }
 
@@ -1928,7 +1984,7 @@ static tb_status set_smem_attr(tb_solver* s) {
       // (measured). The policy above already keeps to 1024 resident threads per SM at 64 registers (__launch_bounds__)
       // and to the shared memory of the SM, and the CTAs split the 512 tensor-memory columns between them (tb_create):
       // for those kernels its own arithmetic stands.
-      if ((TB_TMEM_CODE && m == TB_MEM_STORE_SHARED && !act && TBC_U == 1) || env_int("TB_IGNORE_OCCUPANCY_API", 0)) per_sm = std::max(per_sm, s->blocks_per_sm);
+      if ((TB_TMEM_CODE && m == TB_MEM_STORE_SHARED && TBC_U == 1) || env_int("TB_IGNORE_OCCUPANCY_API", 0)) per_sm = std::max(per_sm, s->blocks_per_sm);
       if (per_sm < s->blocks_per_sm) {
         s->blocks_per_sm = per_sm;
         int blocks = per_sm * s->num_sms;
@@ -2079,7 +2135,7 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   // Tensor memory as the table cache (STORE_SHARED, dense kinds): the resident CTAs of an SM share its 512 columns, a
   // CTA's warps share the CTA's columns by quarter (warp index mod 4), a visit takes two columns. TB_TMEM=0: off.
   P.tmem_cols = 0; P.tmem_visits = 0;
-  if (TB_TMEM_CODE && TBC_U == 1 && s->mem_kind == TB_MEM_STORE_SHARED && !s->active && env_int("TB_TMEM", 1) != 0 && P.nchunks > 0) {
+  if (TB_TMEM_CODE && TBC_U == 1 && s->mem_kind == TB_MEM_STORE_SHARED && env_int("TB_TMEM", 1) != 0 && P.nchunks > 0) {
     int cols = 32;
     while (cols * 2 * s->blocks_per_sm <= 512) cols *= 2;
     const int nwarps = s->threads / 32, per_quarter = (nwarps + 3) / 4;
