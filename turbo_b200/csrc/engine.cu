@@ -263,7 +263,9 @@ __device__ __forceinline__ void decode_word(unsigned long long w, int& a, int& b
   if (!tbd::cls_loads_z(CLS)) c = (c << (32 - TBC_FIELD_BITS)) >> (32 - TBC_FIELD_BITS);
 }
 
-template <int MEM, bool ACT = false>
+// TMALL: every visit of every warp finds its propagator word in tensor memory (the table fits): the sweep is compiled
+// without the L2 path and without the test that chooses between the two.
+template <int MEM, bool ACT = false, bool TMALL = false>
 struct Ctx {
   const DevParams& P;
   Ctl& c;
@@ -634,8 +636,8 @@ struct Ctx {
   //     above spends two more barriers per call on clearing them).
   struct Walk3 {
     int ch;                       // current chunk of this warp (uniform)
-    int widx;                     // index of this lane's first word of the chunk the warp visits after the next one
-    Words cur, nxt;               // this lane's words of the current chunk and of the next one (in flight)
+    int widx;                     // index of this lane's first word of the chunk the warp visits next
+    Words cur;                    // this lane's words of the current chunk (requested at the end of the previous visit)
     unsigned extra;               // evaluations beyond one per visit (WAC1 re-evaluations)
     unsigned pad_evals;           // propagator evaluations spent on padding lanes
     int changed;                  // some visit published a bound
@@ -646,7 +648,7 @@ struct Ctx {
   // The words of the chunk a warp visits `tk` visits into its sweep: from tensor memory when they are there.
   __device__ __forceinline__ Words next_words(const Hot& h, Walk3& w) const {
     Words r;
-    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && __builtin_expect(w.tk < h.tm_visits, 1)) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
+    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && (TMALL || w.tk < h.tm_visits)) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
     else r = load_words(h.words, w.widx);
     ++w.tk;
     return r;
@@ -700,21 +702,10 @@ struct Ctx {
 #pragma unroll
       for (int u = 0; u < TBC_U; ++u) w.notent |= tbd::not_entailed_bits<CLS>(s[u]);
       w.ch += nwarps;
-#ifdef TB_PIN_PREFETCH
-      // `nxt` was requested at the end of the previous visit. A plain register copy is scheduled right behind that
-      // request (at the top of this visit), where it waits for the whole L2 round trip; a funnel shift by an opaque
-      // zero with the visit's last result as its other operand is the same copy, but cannot issue before the visit
-      // is over: the request gets one whole visit to complete.
-#pragma unroll
-      for (int u = 0; u < TBC_U; ++u) {
-        const unsigned lo = __funnelshift_r((unsigned)w.nxt.w[u], (unsigned)w.notent, (unsigned)P.zero);
-        const unsigned hi = __funnelshift_r((unsigned)(w.nxt.w[u] >> 32), (unsigned)w.notent, (unsigned)P.zero);
-        w.cur.w[u] = ((unsigned long long)hi << 32) | lo;
-      }
-#else
-      w.cur = w.nxt;
-#endif
-      w.nxt = next_words(h, w);
+      // (One word in flight, not two: ptxas schedules the copy of a second, prefetched word right behind its request, so
+      // a two-deep register queue has no more distance than this - measured, as is the variant that pins the copy to the
+      // end of the visit: profiles/r02_ab_dense_variants.md. From tensor memory the word is a dozen cycles away anyway.)
+      w.cur = next_words(h, w);
       w.widx += stride;
     } while (w.ch < ce);
     // the class's last chunk is padded with copies of its last propagator: do not count those lanes
@@ -739,8 +730,6 @@ struct Ctx {
       w.widx = (warp * 32 + lane) * TBC_U;
       w.tk = 0;
       w.cur = next_words(h, w);
-      w.widx += stride;
-      w.nxt = next_words(h, w);
       w.widx += stride;
       bool failed = false;
 #define TB_SWEEP(CLS) if (!failed && w.ch < P.cls_begin[CLS + 1]) failed = sweep_class3<CLS>(h, w, wac1, nwarps, stride);
@@ -1398,8 +1387,8 @@ __device__ __forceinline__ Ctl* shared_ctl(Ctl* local) {
   return (Ctl*)r;
 }
 
-template <int MEM, bool ACT>
-__device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned char* dyn) {
+template <int MEM, bool ACT, bool TMALL>
+__device__ __forceinline__ void ctx_init(Ctx<MEM, ACT, TMALL>& k, Ctl* local, unsigned char* dyn) {
   const DevParams& P = k.P;
   k.lc = local;
   if (MEM == TB_MEM_STORE_CLUSTER) {
@@ -1485,8 +1474,8 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT>& k, Ctl* local, unsigned 
   }
 }
 
-template <int MEM, bool ACT>
-__device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
+template <int MEM, bool ACT, bool TMALL>
+__device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT, TMALL>& k) {
   // fold the per-thread / per-warp counters into the block statistics
   unsigned n = k.narrowed;
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -1505,12 +1494,12 @@ __device__ __forceinline__ void ctx_finish(Ctx<MEM, ACT>& k) {
 // ================================================================================================
 
 // The persistent dive-and-solve kernel (gpu_barebones_solve, barebones :620-901).
-template <int MEM, bool ACT = false>
+template <int MEM, bool ACT = false, bool TMALL = false>
 __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_constant__ DevParams P) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM, ACT> k(P, c);
+  Ctx<MEM, ACT, TMALL> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid;
   BlockStats* st = k.st;
@@ -1533,14 +1522,14 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
 }
 
 // One fixpoint per block on caller-provided stores (tb_propagate / tb_propagate_batch).
-template <int MEM, bool ACT = false>
+template <int MEM, bool ACT = false, bool TMALL = false>
 __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_constant__ DevParams P, int nstores,
                                                          const int* in_lb, const int* in_ub,
                                                          int* out_lb, int* out_ub, int* out_failed, int repeat) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM, ACT> k(P, c);
+  Ctx<MEM, ACT, TMALL> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid, T = k.T;
   for (int s = k.slot; s < nstores; s += k.nslots) {
@@ -1580,13 +1569,13 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_
 }
 
 // EPS dive only (tb_dive / tb_dive_batch).
-template <int MEM, bool ACT = false>
+template <int MEM, bool ACT = false, bool TMALL = false>
 __global__ void __launch_bounds__(TB_MAX_THREADS) dive_kernel(const __grid_constant__ DevParams P, unsigned long long first, int count,
                                                     int depth, int* out_lb, int* out_ub, int* out_remaining, int* out_kind) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Ctl c_local;
   Ctl& c = *shared_ctl<MEM>(&c_local);
-  Ctx<MEM, ACT> k(P, c);
+  Ctx<MEM, ACT, TMALL> k(P, c);
   ctx_init(k, &c_local, dyn);
   const int tid = k.tid, T = k.T;
   for (int s = k.slot; s < count; s += k.nslots) {
@@ -1674,6 +1663,7 @@ struct tb_solver {
   TnfLayout layout;                   // device table + variable placement (layout.h)
   std::vector<int32_t> root_lb, root_ub;   // the root domains (precondition check of tb_propagate)
   size_t shared_bytes = 0, store_bytes = 0, prop_bytes = 0;
+  bool tmall = false;                 // every table word of every warp fits in tensor memory (kernel variant without the L2 path)
   bool want_active = false, active = false;   // TB_FP_*_ACTIVE requested / in effect (shared-memory placements)
   int num_sms = 0;
   size_t device_bytes = 0;            // what the solver holds on the device
@@ -1779,16 +1769,19 @@ template <class F>
 static tb_status dispatch(const tb_solver* s, F&& f) {
   using Dense = std::false_type;
   using Active = std::true_type;          // active-set fixpoint: shared-memory placements only
+  using Mixed = std::false_type;          // table words from tensor memory where they fit, from L2 beyond
+  using AllTm = std::true_type;           // the whole table is in tensor memory (s->tmall)
 #ifdef TB_SASS_PROBE      // (developer builds: one instantiation, to read its SASS quickly)
-  return f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{});
+  return f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{}, AllTm{});
 #else
   switch (s->mem_kind) {
-    case TB_MEM_GLOBAL: return f(std::integral_constant<int, TB_MEM_GLOBAL>{}, Dense{});
+    case TB_MEM_GLOBAL: return f(std::integral_constant<int, TB_MEM_GLOBAL>{}, Dense{}, Mixed{});
     case TB_MEM_STORE_SHARED:
-      return s->active ? f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Active{}) : f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{});
+      if (s->active) return f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Active{}, Mixed{});
+      return s->tmall ? f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{}, AllTm{}) : f(std::integral_constant<int, TB_MEM_STORE_SHARED>{}, Dense{}, Mixed{});
     case TB_MEM_TCN_SHARED:
-      return s->active ? f(std::integral_constant<int, TB_MEM_TCN_SHARED>{}, Active{}) : f(std::integral_constant<int, TB_MEM_TCN_SHARED>{}, Dense{});
-    case TB_MEM_STORE_CLUSTER: return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, Dense{});
+      return s->active ? f(std::integral_constant<int, TB_MEM_TCN_SHARED>{}, Active{}, Mixed{}) : f(std::integral_constant<int, TB_MEM_TCN_SHARED>{}, Dense{}, Mixed{});
+    case TB_MEM_STORE_CLUSTER: return f(std::integral_constant<int, TB_MEM_STORE_CLUSTER>{}, Dense{}, Mixed{});
     default: break;
   }
   set_error("unsupported memory kind");
@@ -1941,19 +1934,20 @@ static void place_active(tb_solver* s) {
 }
 
 static tb_status set_smem_attr(tb_solver* s) {
-  return dispatch(s, [&](auto M, auto A) -> tb_status {
+  return dispatch(s, [&](auto M, auto A, auto TM) -> tb_status {
     constexpr int m = decltype(M)::value;
     constexpr bool act = decltype(A)::value;
+    constexpr bool tmall = decltype(TM)::value;
     if (s->shared_bytes) {
-      CU(cudaFuncSetAttribute(solve_kernel<m, act>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
-      CU(cudaFuncSetAttribute(propagate_kernel<m, act>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
-      CU(cudaFuncSetAttribute(dive_kernel<m, act>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(solve_kernel<m, act, tmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(propagate_kernel<m, act, tmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
+      CU(cudaFuncSetAttribute(dive_kernel<m, act, tmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->shared_bytes));
     }
     if (m == TB_MEM_STORE_CLUSTER) {
       if (s->cluster > 8) {
-        CU(cudaFuncSetAttribute(solve_kernel<m, act>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU(cudaFuncSetAttribute(propagate_kernel<m, act>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU(cudaFuncSetAttribute(dive_kernel<m, act>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(solve_kernel<m, act, tmall>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(propagate_kernel<m, act, tmall>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU(cudaFuncSetAttribute(dive_kernel<m, act, tmall>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       }
       cudaLaunchConfig_t cfg = {};
       cfg.blockDim = dim3((unsigned)s->threads);
@@ -1964,7 +1958,7 @@ static tb_status set_smem_attr(tb_solver* s) {
       attr[0].val.clusterDim.x = (unsigned)s->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       int nclusters = 0;
-      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m, act>, &cfg));
+      CU(cudaOccupancyMaxActiveClusters(&nclusters, solve_kernel<m, act, tmall>, &cfg));
       if (nclusters < 1) { set_error("the device cannot host a cluster of this size"); return TB_ERR_UNSUPPORTED; }
       int workers = nclusters;
       if (s->opt.or_blocks > 0) workers = std::min(workers, s->opt.or_blocks);
@@ -1972,10 +1966,10 @@ static tb_status set_smem_attr(tb_solver* s) {
     } else {
       // registers limit the resident CTAs too: ask the driver what really fits (persistent kernel: one wave)
       int per_sm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<m, act>, s->threads, s->shared_bytes));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel<m, act, tmall>, s->threads, s->shared_bytes));
       if (getenv("TB_TRACE_TIMING")) {
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, solve_kernel<m, act>) == cudaSuccess)
+        if (cudaFuncGetAttributes(&fa, solve_kernel<m, act, tmall>) == cudaSuccess)
           fprintf(stderr, "[tb config] solve_kernel<%d,%d>: %d threads, dynamic smem %zu, static smem %zu, %d registers, local %zu B -> %d CTAs per SM by the occupancy API (policy wanted %d)\n",
                   m, (int)act, s->threads, s->shared_bytes, fa.sharedSizeBytes, fa.numRegs, fa.localSizeBytes, per_sm, s->blocks_per_sm);
       }
@@ -2141,6 +2135,9 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
     const int nwarps = s->threads / 32, per_quarter = (nwarps + 3) / 4;
     const int visits_fit = cols / per_quarter / 2, visits_needed = (P.nchunks + nwarps - 1) / nwarps;
     if (cols * s->blocks_per_sm <= 512 && visits_fit >= 1) { P.tmem_cols = cols; P.tmem_visits = std::min(visits_fit, visits_needed); }
+    s->tmall = P.tmem_cols && !s->active && visits_fit >= visits_needed;
+    // (set_smem_attr ran for the mixed variant above; the all-in-TMEM kernels that will be launched need theirs too)
+    if (s->tmall && (rc = set_smem_attr(s)) != TB_OK) return fail(rc);
   }
   pt.mark("kernel attributes, occupancy");
 
@@ -2472,8 +2469,8 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   }
   CU(cudaMemcpyAsync(s->d_cells + TB_CELL_NEXT, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
-  rc = dispatch(s, [&](auto M, auto A) -> tb_status {
-    CU(launch_workers(s, solve_kernel<decltype(M)::value, decltype(A)::value>, s->num_blocks, P));
+  rc = dispatch(s, [&](auto M, auto A, auto TM) -> tb_status {
+    CU(launch_workers(s, solve_kernel<decltype(M)::value, decltype(A)::value, decltype(TM)::value>, s->num_blocks, P));
     CU(cudaGetLastError());
     return TB_OK;
   });
@@ -2659,8 +2656,8 @@ extern "C" tb_status tb_propagate_batch(tb_solver* s, int32_t nstores, const int
   }
   const int repeat = std::max(1, s->opt.propagate_repeat);
   CU(cudaEventRecord(s->ev_start, s->stream));
-  rc = dispatch(s, [&](auto M, auto A) -> tb_status {
-    CU(launch_workers(s, propagate_kernel<decltype(M)::value, decltype(A)::value>, grid, s->P, nstores,
+  rc = dispatch(s, [&](auto M, auto A, auto TM) -> tb_status {
+    CU(launch_workers(s, propagate_kernel<decltype(M)::value, decltype(A)::value, decltype(TM)::value>, grid, s->P, nstores,
                       (const int*)s->d_in_lb, (const int*)s->d_in_ub, s->d_out_lb, s->d_out_ub, s->d_out_i0, repeat));
     CU(cudaGetLastError());
     return TB_OK;
@@ -2704,8 +2701,8 @@ extern "C" tb_status tb_dive_batch(tb_solver* s, uint64_t first, int32_t count, 
   P.cutnodes = 0;
   P.t_start = 0;
   P.npeers = 0; P.steal = 0; P.observe_stop = 0;     // a dive is a pure function of (root, idx): no incumbent, no stop
-  rc = dispatch(s, [&](auto M, auto A) -> tb_status {
-    CU(launch_workers(s, dive_kernel<decltype(M)::value, decltype(A)::value>, grid, P,
+  rc = dispatch(s, [&](auto M, auto A, auto TM) -> tb_status {
+    CU(launch_workers(s, dive_kernel<decltype(M)::value, decltype(A)::value, decltype(TM)::value>, grid, P,
                       (unsigned long long)first, count, depth, s->d_out_lb, s->d_out_ub, s->d_out_i0, s->d_out_i1));
     CU(cudaGetLastError());
     return TB_OK;
