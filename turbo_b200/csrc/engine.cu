@@ -402,6 +402,11 @@ struct Ctx {
       }
     }
     if (!P.split_bits) return;
+    // Waiting is only safe while every CTA of the grid is running: a CTA that has not started yet (the device is shared
+    // with another kernel) needs the slot of one that leaves.
+    // (A grid launched on a free device is complete within microseconds: give it 50 of them.)
+    for (int t = 0; t < 50 && *(volatile unsigned*)(P.split_ctl + TB_SPLIT_STARTED) < (unsigned)nslots; ++t) __nanosleep(1000);
+    if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_STARTED) < (unsigned)nslots) return;
     atomicAdd(P.split_ctl + TB_SPLIT_WAITING, 1u);
     c.counted_idle = 1;
     for (;;) {
@@ -1507,6 +1512,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
     c.task_idx = (unsigned long long)k.slot * (unsigned long long)P.world + (unsigned long long)P.rank;
     c.task_depth = P.subproblems_power; c.task_entry = -1; c.task_j = 0; c.counted_idle = 0; c.abandon = 0; c.task_nodes = 0;
     c.have_task = c.task_idx < P.num_subproblems;
+    if (P.split_bits) atomicAdd(P.split_ctl + TB_SPLIT_STARTED, 1u);
     if (!c.have_task) k.next_subproblem();       // more blocks than subproblems: wait for the tail to be split
     // this run's epoch enters the incumbent cell: whatever an earlier run (of this solver or of a peer) left is void
     atomicMin(P.cells + TB_CELL_BOUND, k.bound_word(TBD_PINF));
@@ -1978,7 +1984,18 @@ static tb_status set_smem_attr(tb_solver* s) {
       // (measured). The policy above already keeps to 1024 resident threads per SM at 64 registers (__launch_bounds__)
       // and to the shared memory of the SM, and the CTAs split the 512 tensor-memory columns between them (tb_create):
       // for those kernels its own arithmetic stands.
-      if ((TB_TMEM_CODE && m == TB_MEM_STORE_SHARED && TBC_U == 1) || env_int("TB_IGNORE_OCCUPANCY_API", 0)) per_sm = std::max(per_sm, s->blocks_per_sm);
+      if ((TB_TMEM_CODE && m == TB_MEM_STORE_SHARED && TBC_U == 1) || env_int("TB_IGNORE_OCCUPANCY_API", 0)) {
+        // (own arithmetic: shared memory was accounted for by configure(); registers and threads here. The grid MUST be
+        // co-resident: blocks that find no work wait for the others - tail splitting - and a CTA that cannot start
+        // because its SM is full of waiting CTAs would never let them finish.)
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, solve_kernel<m, act, tmall>));
+        const cudaDeviceProp* dp = device_props(s->device);
+        const int regs_per_cta = std::max(1, fa.numRegs) * ((s->threads + 31) / 32 * 32);
+        const int by_regs = dp ? std::max(1, dp->regsPerMultiprocessor / regs_per_cta) : 1;
+        const int by_threads = dp ? std::max(1, dp->maxThreadsPerMultiProcessor / s->threads) : 1;
+        per_sm = std::max(per_sm, std::min(s->blocks_per_sm, std::min(by_regs, by_threads)));
+      }
       if (per_sm < s->blocks_per_sm) {
         s->blocks_per_sm = per_sm;
         int blocks = per_sm * s->num_sms;

@@ -63,7 +63,7 @@ struct SplitEntry {
   unsigned pad_[3];
 };
 #define TB_SPLIT_CAP 16384
-enum { TB_SPLIT_N = 0, TB_SPLIT_WAITING = 1, TB_SPLIT_GONE = 2, TB_SPLIT_HINT = 3 };   // words of DevParams::split_ctl
+enum { TB_SPLIT_N = 0, TB_SPLIT_WAITING = 1, TB_SPLIT_GONE = 2, TB_SPLIT_HINT = 3, TB_SPLIT_STARTED = 4 };   // words of DevParams::split_ctl
 
 // Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
 // flattened to plain device pointers (no managed memory, no device-side malloc).
