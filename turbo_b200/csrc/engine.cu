@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/turbo_b200.h"
@@ -184,6 +185,23 @@ struct StoreRef {           // STORE_SHARED / TCN_SHARED: shared memory of this 
     asm volatile("atom.shared.max.s32 %0, [%1], %2;" : "=r"(ol) : "r"(addr(v)), "r"(l) : "memory");
     asm volatile("atom.shared.min.s32 %0, [%1+4], %2;" : "=r"(ou) : "r"(addr(v)), "r"(u) : "memory");
     return l > ol || u < ou;
+  }
+};
+
+// The same shared-memory store addressed by ABSOLUTE shared addresses: the all-in-tensor-memory kernels rewrite the slot
+// fields of their propagator words to `base + 8 * slot` when they fill tensor memory (ctx_init), so the sweep's three
+// address computations per evaluation disappear. Only the sweep uses this view; everything else works on slots.
+struct StoreAbs {
+  __device__ __forceinline__ void ld(int a, int& l, int& u) const {
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(l), "=r"(u) : "r"((unsigned)a));
+  }
+  __device__ __forceinline__ void tell_lb(int a, int n, int old, unsigned& count) const {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, %3;\n\t@p red.shared.max.s32 [%1], %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                 : "+r"(count) : "r"((unsigned)a), "r"(n), "r"(old) : "memory");
+  }
+  __device__ __forceinline__ void tell_ub(int a, int n, int old, unsigned& count) const {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, %3;\n\t@p red.shared.min.s32 [%1+4], %2;\n\t@p add.u32 %0, %0, 1;\n\t}"
+                 : "+r"(count) : "r"((unsigned)a), "r"(n), "r"(old) : "memory");
   }
 };
 
@@ -478,13 +496,11 @@ struct Ctx {
   // What the sweeps touch, copied out of the context into registers for the duration of one fixpoint: the
   // context itself lives in local memory whenever a kernel calls the fixpoint from more than one place, and the
   // volatile accesses of the loop would otherwise re-read its fields from there at every evaluation.
-  struct Hot {
-    StoreRef<MEM> store;
-    const unsigned long long* words;
-    unsigned narrowed;
-    unsigned tm;               // tensor-memory address of this warp's first word (column of visit 0)
-    int tm_visits;             // visits served from tensor memory (0 = none)
-  };
+  // (TMALL: the words in tensor memory carry absolute shared addresses, see StoreAbs)
+  static constexpr bool kAbs = TB_TMEM_CODE && TMALL && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1;
+  struct HotSlots { StoreRef<MEM> store; const unsigned long long* words; unsigned narrowed; unsigned tm; int tm_visits; };
+  struct HotAbs { StoreAbs store; const unsigned long long* words; unsigned narrowed; unsigned tm; int tm_visits; };
+  struct Hot : std::conditional<kAbs, HotAbs, HotSlots>::type {};
 
   struct Walk {
     int ch;                 // current chunk of this warp
@@ -647,22 +663,22 @@ struct Ctx {
     unsigned pad_evals;           // propagator evaluations spent on padding lanes
     int changed;                  // some visit published a bound
     int notent;                   // per lane: non-zero iff some propagator of this lane is not entailed
-    int tk;                       // visit number of the next request (which tensor-memory columns hold its words)
+    unsigned ta;                  // tensor-memory address of the next request's words (two columns per visit)
   };
 
   // The words of the chunk a warp visits `tk` visits into its sweep: from tensor memory when they are there.
   __device__ __forceinline__ Words next_words(const Hot& h, Walk3& w) const {
     Words r;
-    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && (TMALL || w.tk < h.tm_visits)) r.w[0] = tmem_ld64(h.tm + 2u * (unsigned)w.tk);
+    if (TB_TMEM_CODE && TBC_U == 1 && MEM == TB_MEM_STORE_SHARED && (TMALL || w.ta < h.tm + 2u * (unsigned)h.tm_visits)) r.w[0] = tmem_ld64(w.ta);
     else r = load_words(h.words, w.widx);
-    ++w.tk;
+    w.ta += 2u;
     return r;
   }
 
   // Returns true when the store failed (the sweep is over for this warp).
   template <int CLS>
   __device__ __forceinline__ bool sweep_class3(Hot& h, Walk3& w, const bool wac1, const int nwarps, const int stride) {
-    const StoreRef<MEM>& store = h.store;
+    const auto& store = h.store;
     const int ce = P.cls_begin[CLS + 1];
     unsigned last_extra = 0;      // re-evaluations of the latest visit that had work, and which chunk that was
     int last_work_ch = -1;
@@ -723,7 +739,8 @@ struct Ctx {
     const int stride = nwarps * 32 * TBC_U;
     const bool wac1 = P.fixpoint_kind == TB_FP_WAC1 && P.nprops > P.wac1_threshold;
     Hot h;
-    h.store = store; h.words = words; h.narrowed = narrowed;
+    if constexpr (!kAbs) h.store = store;
+    h.words = words; h.narrowed = narrowed;
     // (broadcast from lane 0: the address is warp-uniform, tcgen05.ld takes it from a uniform register)
     h.tm = __shfl_sync(0xffffffffu, tm_warp, 0); h.tm_visits = tm_visits;
     unsigned long long ded = 0;
@@ -733,7 +750,7 @@ struct Ctx {
       Walk3 w;
       w.ch = warp; w.extra = w.pad_evals = 0; w.changed = 0; w.notent = 0;
       w.widx = (warp * 32 + lane) * TBC_U;
-      w.tk = 0;
+      w.ta = h.tm;
       w.cur = next_words(h, w);
       w.widx += stride;
       bool failed = false;
@@ -1021,7 +1038,8 @@ struct Ctx {
     bool pre_failed = P.root_failed != 0;       // a referenced variable is already empty in the root store
     if (P.obj_var >= 0) { int l, u; store.ld(P.obj_var, l, u); pre_failed |= l > u; }
     if (pre_failed) f = F_FAILED;
-    else f = ACT ? fixpoint_active(iters) : dense_fixpoint(iters);
+    else if constexpr (ACT) f = fixpoint_active(iters);
+    else f = dense_fixpoint(iters);
     const bool failed = (f & F_FAILED) != 0;
     const bool solution = !failed && !(f & F_NOT_ENTAILED);
     unsigned long long t1 = 0;
@@ -1460,7 +1478,23 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT, TMALL>& k, Ctl* local, un
     for (int v = 0; v < P.tmem_visits; ++v) {
       const int ch = warp + v * nwarps;
       // (the table is padded behind its end: a chunk index past nchunks reads zeros that are never evaluated)
-      tmem_st64(k.tm_warp + 2u * (unsigned)v, __ldg(P.words + (size_t)ch * 32 + lane));
+      unsigned long long wd = __ldg(P.words + (size_t)ch * 32 + lane);
+      if (Ctx<MEM, ACT, TMALL>::kAbs && ch < P.nchunks) {
+        // slot fields become absolute shared addresses (constants and unused fields stay as they are)
+        int cls = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (cls + step < TBC_NUM && ch >= P.cls_begin[cls + step]) cls += step;
+        const unsigned base = smem_u32(dyn);
+        unsigned long long a = wd & TBC_FIELD_MASK, b = (wd >> TBC_FIELD_BITS) & TBC_FIELD_MASK, cc = (wd >> (2 * TBC_FIELD_BITS)) & TBC_FIELD_MASK;
+        constexpr unsigned kNoX = (1u << TBC_ADD_XK) | (1u << TBC_EQ_T) | (1u << TBC_EQ_F) | (1u << TBC_LEQ_T) | (1u << TBC_LEQ_F);
+        constexpr unsigned kNoZ = (1u << TBC_ADD_ZK) | (1u << TBC_EQ_ZK) | (1u << TBC_LEQ_ZK);
+        if (!((kNoX >> cls) & 1u)) a = base + 8u * (unsigned)a;
+        b = base + 8u * (unsigned)b;
+        if (!((kNoZ >> cls) & 1u)) cc = base + 8u * (unsigned)cc;
+        wd = a | (b << TBC_FIELD_BITS) | (cc << (2 * TBC_FIELD_BITS));
+      }
+      tmem_st64(k.tm_warp + 2u * (unsigned)v, wd);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
@@ -1558,7 +1592,8 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) propagate_kernel(const __grid_
       if (empty_seen) atomicOr(&c.leaf, 1);
       k.sync();
       if (c.leaf) { f = F_FAILED; iters = 0; k.sync(); }
-      else f = ACT ? k.fixpoint_active(iters) : k.dense_fixpoint(iters);
+      else if constexpr (ACT) f = k.fixpoint_active(iters);
+      else f = k.dense_fixpoint(iters);
       if (tid == 0) {
         k.st->fixpoint_iterations += (unsigned long long)iters;
         k.st->nodes++;
