@@ -270,6 +270,18 @@ __device__ __forceinline__ void init_store_ref<TB_MEM_STORE_CLUSTER>(StoreRef<TB
   st.base = smem_u32(dyn); st.lc = P.cluster_log2; st.cmask = (unsigned)P.cluster_size - 1u;
 }
 
+// A device propagator word with its slot fields rewritten to absolute shared addresses (`base` = address of slot 0);
+// constants and unused fields stay as they are. `cls` is the class of the word's chunk.
+__device__ __forceinline__ unsigned long long word_to_abs(unsigned long long wd, int cls, unsigned base) {
+  unsigned long long a = wd & TBC_FIELD_MASK, b = (wd >> TBC_FIELD_BITS) & TBC_FIELD_MASK, cc = (wd >> (2 * TBC_FIELD_BITS)) & TBC_FIELD_MASK;
+  constexpr unsigned kNoX = (1u << TBC_ADD_XK) | (1u << TBC_EQ_T) | (1u << TBC_EQ_F) | (1u << TBC_LEQ_T) | (1u << TBC_LEQ_F);
+  constexpr unsigned kNoZ = (1u << TBC_ADD_ZK) | (1u << TBC_EQ_ZK) | (1u << TBC_LEQ_ZK);
+  if (!((kNoX >> cls) & 1u)) a = base + 8u * (unsigned)a;
+  b = base + 8u * (unsigned)b;
+  if (!((kNoZ >> cls) & 1u)) cc = base + 8u * (unsigned)cc;
+  return a | (b << TBC_FIELD_BITS) | (cc << (2 * TBC_FIELD_BITS));
+}
+
 // The three 21-bit fields of a device propagator word (tnf_classes.h); constants are sign-extended.
 template <int CLS>
 __device__ __forceinline__ void decode_word(unsigned long long w, int& a, int& b, int& c) {
@@ -497,7 +509,11 @@ struct Ctx {
   // context itself lives in local memory whenever a kernel calls the fixpoint from more than one place, and the
   // volatile accesses of the loop would otherwise re-read its fields from there at every evaluation.
   // (TMALL: the words in tensor memory carry absolute shared addresses, see StoreAbs)
-  static constexpr bool kAbs = TB_TMEM_CODE && TMALL && MEM == TB_MEM_STORE_SHARED && !ACT && TBC_U == 1;
+#ifdef TB_FIXPOINT_V2
+  static constexpr bool kAbs = false;       // (round 1's loop works on slots)
+#else
+  static constexpr bool kAbs = !ACT && TBC_U == 1 && ((TB_TMEM_CODE && TMALL && MEM == TB_MEM_STORE_SHARED) || MEM == TB_MEM_TCN_SHARED);
+#endif
   struct HotSlots { StoreRef<MEM> store; const unsigned long long* words; unsigned narrowed; unsigned tm; int tm_visits; };
   struct HotAbs { StoreAbs store; const unsigned long long* words; unsigned narrowed; unsigned tm; int tm_visits; };
   struct Hot : std::conditional<kAbs, HotAbs, HotSlots>::type {};
@@ -1480,19 +1496,11 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT, TMALL>& k, Ctl* local, un
       // (the table is padded behind its end: a chunk index past nchunks reads zeros that are never evaluated)
       unsigned long long wd = __ldg(P.words + (size_t)ch * 32 + lane);
       if (Ctx<MEM, ACT, TMALL>::kAbs && ch < P.nchunks) {
-        // slot fields become absolute shared addresses (constants and unused fields stay as they are)
         int cls = 0;
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1)
           if (cls + step < TBC_NUM && ch >= P.cls_begin[cls + step]) cls += step;
-        const unsigned base = smem_u32(dyn);
-        unsigned long long a = wd & TBC_FIELD_MASK, b = (wd >> TBC_FIELD_BITS) & TBC_FIELD_MASK, cc = (wd >> (2 * TBC_FIELD_BITS)) & TBC_FIELD_MASK;
-        constexpr unsigned kNoX = (1u << TBC_ADD_XK) | (1u << TBC_EQ_T) | (1u << TBC_EQ_F) | (1u << TBC_LEQ_T) | (1u << TBC_LEQ_F);
-        constexpr unsigned kNoZ = (1u << TBC_ADD_ZK) | (1u << TBC_EQ_ZK) | (1u << TBC_LEQ_ZK);
-        if (!((kNoX >> cls) & 1u)) a = base + 8u * (unsigned)a;
-        b = base + 8u * (unsigned)b;
-        if (!((kNoZ >> cls) & 1u)) cc = base + 8u * (unsigned)cc;
-        wd = a | (b << TBC_FIELD_BITS) | (cc << (2 * TBC_FIELD_BITS));
+        wd = word_to_abs(wd, cls, smem_u32(dyn));
       }
       tmem_st64(k.tm_warp + 2u * (unsigned)v, wd);
     }
@@ -1510,6 +1518,19 @@ __device__ __forceinline__ void ctx_init(Ctx<MEM, ACT, TMALL>& k, Ctl* local, un
     }
     if (bytes) { while (!mbar_try_wait(&local->mbar, k.mbar_phase)) {} k.mbar_phase ^= 1; }
     k.words = (const unsigned long long*)sprops;
+    if (Ctx<MEM, ACT, TMALL>::kAbs) {
+      // the staged copy is this CTA's own: rewrite its slot fields to absolute shared addresses (see StoreAbs)
+      unsigned long long* tw = (unsigned long long*)sprops;
+      for (int i = threadIdx.x; i < P.nchunks * 32; i += blockDim.x) {
+        const int ch = i >> 5;
+        int cls = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (cls + step < TBC_NUM && ch >= P.cls_begin[cls + step]) cls += step;
+        tw[i] = word_to_abs(tw[i], cls, smem_u32(dyn));
+      }
+      k.sync();
+    }
   }
 }
 
