@@ -143,6 +143,36 @@ def test_an_idle_gpu_steals_from_its_peers(eng):
     assert all(r["stats"]["eps_stolen_subproblems"] == 0 for r in res)
 
 
+def test_the_tail_is_shared_between_the_gpus(eng, monkeypatch):
+    """One subproblem for two GPUs: rank 1 has nothing of its own, its blocks wait, rank 0's busy block splits its
+    subproblem and rank 1 takes children out of rank 0's pool (peer-mapped with the cell block). The search is still
+    exhaustive and ends on the reference's optimum."""
+    monkeypatch.setenv("TB_SPLIT_MIN_NODES", "256")
+    for name in ("pat13", "triangular9"):
+        pb, info = golden_io.load(name)
+        solvers = [eng.Solver(pb, device=g, gpu_rank=g, gpu_world=2, subproblems_power=0, timeout_ms=60000) for g in range(2)]
+        eng.link_peers(solvers)
+        res = run_all(solvers)
+        m = eng.result_reduce([s.result_pack() for s in solvers])
+        for s in solvers:
+            s.close()
+        assert m["has_solution"] and m["exhaustive"], name
+        assert golden_io.user_objective(info, m["lb"], m["ub"]) == info["expected"], name
+        assert res[0]["stats"]["eps_split_subproblems"] > 0
+        assert res[1]["stats"]["eps_stolen_subproblems"] > 0 and res[1]["stats"]["nodes"] > 0
+    # TB_SHARE_SPLIT=0 at link time: every GPU keeps its tail to itself, same answer
+    monkeypatch.setenv("TB_SHARE_SPLIT", "0")
+    pb, info = golden_io.load("pat13")
+    solvers = [eng.Solver(pb, device=g, gpu_rank=g, gpu_world=2, subproblems_power=0, timeout_ms=60000) for g in range(2)]
+    eng.link_peers(solvers)
+    res = run_all(solvers)
+    m = eng.result_reduce([s.result_pack() for s in solvers])
+    for s in solvers:
+        s.close()
+    assert m["exhaustive"] and golden_io.user_objective(info, m["lb"], m["ub"]) == info["expected"]
+    assert res[1]["stats"]["eps_stolen_subproblems"] == 0
+
+
 def test_first_solution_of_a_satisfaction_problem_stops_every_gpu(eng):
     n = min(eng.device_count(), 8)
     pb = tnf_gen.planted(60, 80, 5, objective=False)

@@ -135,6 +135,7 @@ struct Ctl {                       // per-CTA control block in static shared mem
   unsigned long long task_idx;     // the subproblem being solved: dive to index task_idx at depth task_depth
   int task_depth;                  // P.subproblems_power, or deeper for a child of a subproblem that was split at the tail
   int task_entry;                  // -1, or the pool entry the child comes from
+  int task_src;                    // whose pool that is: -1 this GPU's, else the peer's index
   unsigned task_j;                 // its number inside that entry
   int have_task;                   // next_subproblem() found work
   unsigned task_nodes;             // nodes spent on this subproblem so far
@@ -370,26 +371,64 @@ struct Ctx {
       v = old;
     }
   }
-  // One child of a split subproblem, if there is an open entry in the pool.
-  __device__ __forceinline__ bool take_split() {
-    if (!P.split_bits) return false;
-    const unsigned n = min(*(volatile unsigned*)(P.split_ctl + TB_SPLIT_N), (unsigned)TB_SPLIT_CAP);
+  // The control block and the pool behind a cell block (this GPU's or a peer's).
+  __device__ __forceinline__ static unsigned* split_ctl_of(unsigned long long* cb) { return (unsigned*)(cb + TB_CELL_SPLIT); }
+  __device__ __forceinline__ static SplitEntry* split_pool_of(unsigned long long* cb) { return (SplitEntry*)(cb + TB_CELL_WORDS); }
+
+  // One child of a split subproblem from the pool behind `cb` (src = -1: this GPU's; else peer `src`'s, over NVLink).
+  __device__ __forceinline__ bool take_split_from(unsigned long long* cb, int src) {
+    unsigned* ctl = split_ctl_of(cb);
+    if (src >= 0 && *(volatile unsigned*)(ctl + TB_SPLIT_EPOCH) != P.epoch) return false;      // the peer is in another run
+    SplitEntry* pool = split_pool_of(cb);
+    const unsigned n = min(*(volatile unsigned*)(ctl + TB_SPLIT_N), (unsigned)TB_SPLIT_CAP);
     unsigned first_open = n;
-    for (unsigned i = *(volatile unsigned*)(P.split_ctl + TB_SPLIT_HINT); i < n; ++i) {
-      SplitEntry* e = P.split_pool + i;
+    for (unsigned i = *(volatile unsigned*)(ctl + TB_SPLIT_HINT); i < n; ++i) {
+      SplitEntry* e = pool + i;
       const unsigned cnt = *(volatile unsigned*)&e->count;
       if (cnt == 0) { first_open = min(first_open, i); continue; }            // being written
       if (*(volatile unsigned*)&e->next >= cnt) continue;
       first_open = min(first_open, i);
-      const unsigned j = atomicAdd(&e->next, 1u);
+      if (*(volatile unsigned*)&e->epoch != P.epoch) continue;
+      const unsigned j = src < 0 ? atomicAdd(&e->next, 1u) : atomicAdd_system(&e->next, 1u);
       if (j < cnt) {
-        c.task_idx = e->base + (unsigned long long)j; c.task_depth = e->depth; c.task_entry = (int)i; c.task_j = j;
+        c.task_idx = e->base + (unsigned long long)j; c.task_depth = e->depth; c.task_entry = (int)i; c.task_j = j; c.task_src = src;
         c.have_task = 1;
         return true;
       }
     }
-    if (first_open > *(volatile unsigned*)(P.split_ctl + TB_SPLIT_HINT)) atomicMax(P.split_ctl + TB_SPLIT_HINT, first_open);
+    if (first_open > *(volatile unsigned*)(ctl + TB_SPLIT_HINT)) {
+      if (src < 0) atomicMax(ctl + TB_SPLIT_HINT, first_open); else atomicMax_system(ctl + TB_SPLIT_HINT, first_open);
+    }
     return false;
+  }
+  __device__ __forceinline__ bool take_split(bool peers = true) {
+    if (!P.split_bits) return false;
+    if (take_split_from(P.cells, -1)) return true;
+    if (P.share_split && peers)
+      for (int t = 0; t < P.npeers; ++t) { const int g = (slot + t) % P.npeers; if (take_split_from(P.peer_cells[g], g)) { st->eps_stolen += 1; return true; } }
+    return false;
+  }
+  // Somebody - on this GPU or on a linked one - is waiting for work.
+  __device__ __forceinline__ bool somebody_waits() const {
+    if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) > 0u) return true;
+    if (P.share_split)
+      for (int g = 0; g < P.npeers; ++g) {
+        volatile unsigned* ctl = split_ctl_of(P.peer_cells[g]);
+        if (ctl[TB_SPLIT_EPOCH] == P.epoch && ctl[TB_SPLIT_WAITING] > 0u) return true;
+      }
+    return false;
+  }
+  // Every block of every linked GPU (of this run) is waiting or gone: the search is over. A peer whose control block
+  // carries another epoch has not started this run yet (or never will): during `grace` it counts as busy.
+  __device__ __forceinline__ bool everybody_idle(bool grace) const {
+    if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) + *(volatile unsigned*)(P.split_ctl + TB_SPLIT_GONE) < (unsigned)nslots) return false;
+    if (P.share_split)
+      for (int g = 0; g < P.npeers; ++g) {
+        volatile unsigned* ctl = split_ctl_of(P.peer_cells[g]);
+        if (ctl[TB_SPLIT_EPOCH] != P.epoch) { if (grace) return false; continue; }
+        if (ctl[TB_SPLIT_WAITING] + ctl[TB_SPLIT_GONE] < ctl[TB_SPLIT_NSLOTS]) return false;
+      }
+    return true;
   }
 
   // The subproblem this block has been working on becomes 2^split_bits children in the pool (thread 0).
@@ -397,8 +436,8 @@ struct Ctx {
     const unsigned i = atomicAdd(P.split_ctl + TB_SPLIT_N, 1u);
     if (i >= (unsigned)TB_SPLIT_CAP) return false;
     SplitEntry* e = P.split_pool + i;
-    e->base = c.task_idx << P.split_bits; e->depth = c.task_depth + P.split_bits; e->next = 0u;
-    __threadfence();
+    e->base = c.task_idx << P.split_bits; e->depth = c.task_depth + P.split_bits; e->next = 0u; e->epoch = P.epoch;
+    __threadfence_system();
     *(volatile unsigned*)&e->count = 1u << P.split_bits;
     if (c.task_entry < 0) st->eps_split += 1;      // (a child that is split again is counted with neither)
     return true;
@@ -410,7 +449,7 @@ struct Ctx {
   // the busy blocks split), until work appears or every block of the grid is waiting or gone. Thread 0.
   __device__ __forceinline__ void next_subproblem() {
     const unsigned long long world = (unsigned long long)P.world;
-    c.have_task = 0; c.task_entry = -1; c.task_depth = P.subproblems_power;
+    c.have_task = 0; c.task_entry = -1; c.task_src = -1; c.task_depth = P.subproblems_power;
     const unsigned long long k = atomicAdd(P.cells + TB_CELL_NEXT, 1ull) & TB_K_MASK;
     if (k * world + (unsigned long long)P.rank < P.num_subproblems) { c.task_idx = k * world + (unsigned long long)P.rank; c.have_task = 1; return; }
     if (take_split()) return;
@@ -439,10 +478,13 @@ struct Ctx {
     if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_STARTED) < (unsigned)nslots) return;
     atomicAdd(P.split_ctl + TB_SPLIT_WAITING, 1u);
     c.counted_idle = 1;
-    for (;;) {
+    // (this GPU's pool is polled every 2 us, the peers' - over NVLink - every 16 us)
+    const unsigned long long t0 = globaltimer_ns();
+    for (unsigned it = 0;; ++it) {
       if (stop_raised()) return;
-      if (take_split()) { atomicSub(P.split_ctl + TB_SPLIT_WAITING, 1u); c.counted_idle = 0; return; }
-      if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) + *(volatile unsigned*)(P.split_ctl + TB_SPLIT_GONE) >= (unsigned)nslots) return;
+      const bool far = (it & 7u) == 0u;
+      if (take_split(far)) { atomicSub(P.split_ctl + TB_SPLIT_WAITING, 1u); c.counted_idle = 0; return; }
+      if ((far || !P.share_split) && everybody_idle(globaltimer_ns() - t0 < 20000000ull)) return;
       __nanosleep(2000);
     }
   }
@@ -1259,8 +1301,8 @@ struct Ctx {
           // E. a leaf above the subproblem depth: skip the whole subtree (:718-741)
           if (tid == 0 && c.task_entry >= 0) {
             // a child of a split subproblem: its siblings below the same leaf need no dive either
-            SplitEntry* e = P.split_pool + c.task_entry;
-            if (remaining < 31) atomicMax(&e->next, min(e->count, ((c.task_j >> remaining) + 1u) << remaining));
+            SplitEntry* e = split_pool_of(c.task_src < 0 ? P.cells : P.peer_cells[c.task_src]) + c.task_entry;
+            if (remaining < 31) atomicMax_system(&e->next, min(e->count, ((c.task_j >> remaining) + 1u) << remaining));
           } else if (tid == 0) {
             // nobody needs to dive into [idx, next) any more: advance every shard's dispenser past it
             const unsigned long long next = ((idx >> remaining) + 1ull) << remaining;
@@ -1293,7 +1335,7 @@ struct Ctx {
           }
           // tail splitting: somebody is waiting for work and this subproblem has been going on for a while
           if (tid == 0 && P.split_bits && ++c.task_nodes >= (unsigned)P.split_min_nodes && (c.task_nodes & 255u) == 0u &&
-              *(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) > 0u && c.task_depth + P.split_bits <= 56 &&
+              somebody_waits() && c.task_depth + P.split_bits <= 56 &&
               *(volatile unsigned*)(P.split_ctl + TB_SPLIT_N) < (unsigned)TB_SPLIT_CAP)
             c.abandon = push_split() ? 1 : 0;
           sync();
@@ -1565,7 +1607,7 @@ __global__ void __launch_bounds__(TB_MAX_THREADS) solve_kernel(const __grid_cons
   BlockStats* st = k.st;
   if (tid == 0) {
     c.task_idx = (unsigned long long)k.slot * (unsigned long long)P.world + (unsigned long long)P.rank;
-    c.task_depth = P.subproblems_power; c.task_entry = -1; c.task_j = 0; c.counted_idle = 0; c.abandon = 0; c.task_nodes = 0;
+    c.task_depth = P.subproblems_power; c.task_entry = -1; c.task_src = -1; c.task_j = 0; c.counted_idle = 0; c.abandon = 0; c.task_nodes = 0;
     c.have_task = c.task_idx < P.num_subproblems;
     if (P.split_bits) atomicAdd(P.split_ctl + TB_SPLIT_STARTED, 1u);
     if (!c.have_task) k.next_subproblem();       // more blocks than subproblems: wait for the tail to be split
@@ -1797,7 +1839,7 @@ static unsigned long long* acquire_cells(int device) {
     }
   }
   unsigned long long* p = nullptr;
-  if (cudaMalloc((void**)&p, TB_CELL_WORDS * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMalloc((void**)&p, TB_CELL_BLOCK_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   return p;
 }
 static void release_cells(int device, unsigned long long* p) {
@@ -2093,8 +2135,9 @@ static tb_status ensure_scratch(tb_solver* s, int slots) {
   }
   if ((rc = dev_alloc(s, &P.stats, (size_t)slots))) return rc;
   if (!P.split_pool) {
-    if ((rc = dev_alloc(s, &P.split_pool, (size_t)TB_SPLIT_CAP))) return rc;
-    if ((rc = dev_alloc(s, &P.split_ctl, 8))) return rc;
+    // (control block and pool live in the cell block's allocation: the peers map them with the same IPC handle)
+    P.split_ctl = (unsigned*)(s->d_cells + TB_CELL_SPLIT);
+    P.split_pool = (SplitEntry*)(s->d_cells + TB_CELL_WORDS);
     P.split_bits = std::max(0, std::min(12, env_int("TB_SPLIT_BITS", 6)));
     P.split_min_nodes = std::max(256, env_int("TB_SPLIT_MIN_NODES", 4096));
   }
@@ -2539,6 +2582,8 @@ extern "C" tb_status tb_solve(tb_solver* s, volatile int32_t* stop_flag, int32_t
   if (P.split_bits) {
     CU(cudaMemsetAsync(P.split_ctl, 0, 8 * sizeof(unsigned), s->stream));
     CU(cudaMemsetAsync(P.split_pool, 0, sizeof(SplitEntry) * (size_t)TB_SPLIT_CAP, s->stream));
+    const unsigned who[2] = {(unsigned)s->num_blocks, P.epoch};          // TB_SPLIT_NSLOTS, TB_SPLIT_EPOCH: written last
+    CU(cudaMemcpyAsync(P.split_ctl + TB_SPLIT_NSLOTS, who, sizeof(who), cudaMemcpyHostToDevice, s->stream));
   }
   CU(cudaMemcpyAsync(s->d_cells + TB_CELL_NEXT, &first_free, sizeof(first_free), cudaMemcpyHostToDevice, s->stream));
   CU(cudaEventRecord(s->ev_start, s->stream));
@@ -2805,6 +2850,8 @@ static tb_status publish_peers(tb_solver* s) {
   P.npeers = (int)s->peer_cells.size();
   // stealing needs every other shard's dispenser (TB_STEAL=0 keeps the static shards)
   P.steal = (P.npeers == P.world - 1 && env_int("TB_STEAL", 1) != 0) ? 1u : 0u;
+  // ... and the tail: idle blocks take children of subproblems a peer has split (TB_SHARE_SPLIT=0: every GPU its own tail)
+  P.share_split = (P.steal && env_int("TB_SHARE_SPLIT", 1) != 0) ? 1 : 0;
   return TB_OK;
 }
 

@@ -36,7 +36,11 @@ struct BlockStats {
 #define TB_CELL_NEXT 1
 #define TB_CELL_STOP 2
 #define TB_CELL_STREAM 3      // number of improving solutions streamed so far in this run (tb_stream_solutions)
+#define TB_CELL_SPLIT 4       // words 4..7: the control block of the tail-splitting pool (8 unsigned, TB_SPLIT_*)
 #define TB_CELL_WORDS 16
+// The allocation behind a cell block continues with the pool itself (TB_SPLIT_CAP entries of 32 bytes at byte 128): one
+// CUDA IPC handle maps cells, control block and pool into the peers, whose idle blocks take children from it too.
+#define TB_CELL_BLOCK_BYTES (TB_CELL_WORDS * 8 + TB_SPLIT_CAP * 32)
 #define TB_MAX_PEERS 31
 #define TB_K_BITS 40
 #define TB_K_MASK ((1ull << TB_K_BITS) - 1ull)
@@ -60,10 +64,12 @@ struct SplitEntry {
   int depth;                    // dive depth of the children
   unsigned count;               // number of children (0 = entry not published yet)
   unsigned next;                // dispenser over the children (fetch-add; monotone max on a failed subtree)
-  unsigned pad_[3];
+  unsigned epoch;               // the run the entry belongs to (a peer of another run leaves it alone)
+  unsigned pad_[2];
 };
 #define TB_SPLIT_CAP 16384
-enum { TB_SPLIT_N = 0, TB_SPLIT_WAITING = 1, TB_SPLIT_GONE = 2, TB_SPLIT_HINT = 3, TB_SPLIT_STARTED = 4 };   // words of DevParams::split_ctl
+// words of the split control block (unsigned), which lives in the cell block (TB_CELL_SPLIT) so that the peers see it
+enum { TB_SPLIT_N = 0, TB_SPLIT_WAITING = 1, TB_SPLIT_GONE = 2, TB_SPLIT_HINT = 3, TB_SPLIT_STARTED = 4, TB_SPLIT_NSLOTS = 5, TB_SPLIT_EPOCH = 6 };
 
 // Kernel parameters: what UnifiedData + GridData carry in the reference (barebones :57-78, 409-453),
 // flattened to plain device pointers (no managed memory, no device-side malloc).
@@ -107,9 +113,10 @@ struct DevParams {
   const int* watch_list;                 // chunk ids, ascending per slot
   const unsigned long long* watch_inline; // per slot: its first three watchers as 16-bit chunk ids (0xFFFF = none), top 16 bits 0xFFFE = more in the CSR list
   // tail splitting (see SplitEntry)
-  SplitEntry* split_pool;                // [TB_SPLIT_CAP]
-  unsigned* split_ctl;                   // entries appended / blocks waiting for work / blocks gone / lowest open entry
+  SplitEntry* split_pool;                // [TB_SPLIT_CAP], behind this GPU's cell block
+  unsigned* split_ctl;                   // entries appended / blocks waiting for work / blocks gone / lowest open entry / ...
   int split_bits, split_min_nodes;       // e (0 = off) and the node count after which a subproblem may be given up
+  int share_split, pad5_;                // idle blocks also take children from the peers' pools
   // intermediate solutions (tb_stream_solutions): ring of store images in device memory + records in mapped host memory
   int* stream_img;                       // [stream_slots] images of 2 * vpad ints
   StreamRec* stream_rec;                 // [stream_slots], pinned host memory
