@@ -159,7 +159,7 @@ def test_the_tail_is_shared_between_the_gpus(eng, monkeypatch):
         assert m["has_solution"] and m["exhaustive"], name
         assert golden_io.user_objective(info, m["lb"], m["ub"]) == info["expected"], name
         assert res[0]["stats"]["eps_split_subproblems"] > 0
-        assert res[1]["stats"]["eps_stolen_subproblems"] > 0 and res[1]["stats"]["nodes"] > 0
+        assert res[1]["stats"]["eps_split_parts_solved"] > 0 and res[1]["stats"]["nodes"] > 0      # children of rank 0's subproblem
     # TB_SHARE_SPLIT=0 at link time: every GPU keeps its tail to itself, same answer
     monkeypatch.setenv("TB_SHARE_SPLIT", "0")
     pb, info = golden_io.load("pat13")
@@ -170,7 +170,7 @@ def test_the_tail_is_shared_between_the_gpus(eng, monkeypatch):
     for s in solvers:
         s.close()
     assert m["exhaustive"] and golden_io.user_objective(info, m["lb"], m["ub"]) == info["expected"]
-    assert res[1]["stats"]["eps_stolen_subproblems"] == 0
+    assert res[1]["stats"]["eps_split_parts_solved"] == 0
 
 
 def test_first_solution_of_a_satisfaction_problem_stops_every_gpu(eng):

@@ -405,7 +405,7 @@ struct Ctx {
     if (!P.split_bits) return false;
     if (take_split_from(P.cells, -1)) return true;
     if (P.share_split && peers)
-      for (int t = 0; t < P.npeers; ++t) { const int g = (slot + t) % P.npeers; if (take_split_from(P.peer_cells[g], g)) { st->eps_stolen += 1; return true; } }
+      for (int t = 0; t < P.npeers; ++t) { const int g = (slot + t) % P.npeers; if (take_split_from(P.peer_cells[g], g)) return true; }
     return false;
   }
   // Somebody - on this GPU or on a linked one - is waiting for work.
