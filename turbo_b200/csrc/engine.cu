@@ -79,9 +79,10 @@ __device__ __forceinline__ void bulk_s2g_issue(void* gdst, const void* ssrc, uns
 }
 // The issuing thread may overwrite the shared source as soon as the copy engine has READ it; the global writes are
 // only waited for (bulk_wait_all) by whoever reads an image back or leaves the kernel.
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_commit_wait_read() { bulk_commit(); bulk_wait_read(); }
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -1158,34 +1159,8 @@ struct Ctx {
     return ((unsigned long long)hi << 32) | (unsigned)i;
   }
 
-  // What thread 0 does before a node of the subproblem is propagated: I. inject the incumbent bound, detect an
-  // unconstrained objective; then the tail-splitting trigger (somebody is waiting for work and this subproblem has been
-  // going on for a while). Sets c.stop / c.abandon, which everybody reads after the barrier that follows.
-  __device__ __forceinline__ void node_prologue() {
-    if (P.obj_var >= 0) {
-      int appx = read_bound();
-      if (appx != TBD_PINF) {
-        bool moved = store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
-        moved |= store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
-        if (moved) mark_var(P.obj_var);
-      }
-      if (appx == TBD_NINF) { c.stop = 1; raise_stop(true); }
-    }
-    if (P.split_bits && ++c.task_nodes >= (unsigned)P.split_min_nodes && (c.task_nodes & 255u) == 0u &&
-        somebody_waits() && c.task_depth + P.split_bits <= 56 &&
-        *(volatile unsigned*)(P.split_ctl + TB_SPLIT_N) < (unsigned)TB_SPLIT_CAP)
-      c.abandon = push_split() ? 1 : 0;
-  }
-
-  // The snapshot of a node is requested BEFORE its decision is chosen (single-CTA shared placements): the copy engine
-  // reads the store while the block scans the strategy, and thread 0 only has to see the read finished before it
-  // applies the decision.
-  static constexpr bool kEarlySnap = MEM == TB_MEM_STORE_SHARED || MEM == TB_MEM_TCN_SHARED;
-
-  // thread 0 only. `take_left` >= -1: the search (not the dive) - the left branch is taken at once, in the same serial
-  // section: wait for the snapshot of depth `take_left` (if >= 0) to have been read, tag it, apply the decision, run
-  // the prologue of the child node. One barrier (split()'s last) then covers all of it.
-  __device__ __forceinline__ void push_decision(int val_order, int var, const int take_left = -2) {
+  // thread 0 only
+  __device__ __forceinline__ void push_decision(int val_order, int var) {
     if (c.depth >= P.max_depth) { st->error = TB_ERR_DEPTH; st->exhaustive = 0; c.stop = 1; raise_stop(false); c.pushed = 0; return; }
     int l, u; store.ld(var, l, u);
     Decision d;
@@ -1200,20 +1175,13 @@ struct Ctx {
     d.rope0 = c.depth + 1;
     if (c.depth > 0) { const Decision& p = dec[c.depth - 1]; d.rope1 = p.cur == 0 ? p.rope0 : p.rope1; }
     else d.rope1 = -1;
-    if (take_left >= -1) d.cur = 0;
     dec[c.depth] = d;
     c.depth++;
     c.pushed = 1;
-    if (take_left >= -1) {
-      if (take_left >= 0) { bulk_wait_read(); g_snap_tag[take_left % P.nsnap] = take_left; }
-      store.embed(d.var, d.clb0, d.cub0);
-      mark_var(d.var);
-      node_prologue();
-    }
   }
 
   // Returns (uniformly) whether a decision was pushed at dec[depth-1].
-  __device__ __forceinline__ bool split(const int take_left = -2) {
+  __device__ __forceinline__ bool split() {
     const int lane = tid & 31;
     for (;;) {
       const int s = c.cur_strategy;       // uniform (barrier before every read)
@@ -1248,7 +1216,7 @@ struct Ctx {
         if (best != ~0ull) {
           c.next_unassigned = c.sel_first[par];
           int i = (int)(unsigned)(best & 0xffffffffu);
-          push_decision(strat.val_order, in_store ? i : strat.vars[i], take_left);
+          push_decision(strat.val_order, in_store ? i : strat.vars[i]);
         } else {
           c.cur_strategy = s + 1;
           c.next_unassigned = 0;
@@ -1347,19 +1315,33 @@ struct Ctx {
           }
           mode = M_NEXT;
         } else if (!c.stop) {
-          if (tid == 0) {
-            if (P.has_eps_strategy) { c.cur_strategy = max(1, c.cur_strategy); c.next_unassigned = 0; }
-            node_prologue();
-          }
+          if (tid == 0 && P.has_eps_strategy) { c.cur_strategy = max(1, c.cur_strategy); c.next_unassigned = 0; }
           sync();
           mode = M_SOLVE;
         } else mode = M_NEXT;
       }
       if (mode == M_SOLVE) {
-        // (the prologue of this node ran in the serial section that produced it: after the dive above, with the decision
-        // in push_decision, with the backtrack below - always followed by a barrier)
         if (c.stop) mode = M_SOLVE_END;
-        else if (c.abandon) mode = M_NEXT;          // its children are in the pool now; this block takes one of them
+        else {
+          // I. inject the incumbent bound (thread 0), detect an unconstrained objective
+          if (tid == 0 && P.obj_var >= 0) {
+            int appx = read_bound();
+            if (appx != TBD_PINF) {
+              bool moved = store.embed(P.obj_var, TBD_NINF, tbd::pred(appx));
+              moved |= store.embed(P.obj_var, TBD_NINF, tbd::pred(c.best_bound));
+              if (moved) mark_var(P.obj_var);
+            }
+            if (appx == TBD_NINF) { c.stop = 1; raise_stop(true); }
+          }
+          // tail splitting: somebody is waiting for work and this subproblem has been going on for a while
+          if (tid == 0 && P.split_bits && ++c.task_nodes >= (unsigned)P.split_min_nodes && (c.task_nodes & 255u) == 0u &&
+              somebody_waits() && c.task_depth + P.split_bits <= 56 &&
+              *(volatile unsigned*)(P.split_ctl + TB_SPLIT_N) < (unsigned)TB_SPLIT_CAP)
+            c.abandon = push_split() ? 1 : 0;
+          sync();
+          if (c.stop) mode = M_SOLVE_END;
+          else if (c.abandon) mode = M_NEXT;          // its children are in the pool now; this block takes one of them
+        }
       }
       if (mode == M_SOLVE_END) {
         sync();
@@ -1402,27 +1384,14 @@ struct Ctx {
             if (tid == 0) { c.snap_strategy = c.cur_strategy; c.snap_next_unassigned = c.next_unassigned; }
             sync();
           }
-          // copying instead of recomputation: keep this node's fixpoint, so that the right branch of the decision
-          // restarts from here (one changed variable) instead of from the subproblem root plus a replay
-          const int j0 = c.depth;
-          if (kEarlySnap && P.nsnap && threadIdx.x == 0) {
-            // (propagate() ended on a barrier: the store is final. The slot's old image is gone from here on.)
-            g_snap_tag[j0 % P.nsnap] = -1;
-            char* dst = (char*)(g_snap + (size_t)(j0 % P.nsnap) * 2 * P.vpad);
-            const unsigned bytes = (unsigned)P.vpad * 8u;
-            fence_proxy_async();
-            for (unsigned off = 0; off < bytes; off += BULK_CHUNK)
-              bulk_s2g_issue(dst + off, (const char*)sdyn + off, min(BULK_CHUNK, bytes - off));
-            bulk_commit();
-          }
-          bool pushed = split(kEarlySnap ? (P.nsnap ? j0 : -1) : -2);
+          bool pushed = split();
           if (pushed && P.nsnap) {
+            // copying instead of recomputation: keep this node's fixpoint, so that the right branch of the decision
+            // restarts from here (one changed variable) instead of from the subproblem root plus a replay
             const int j = c.depth - 1;
-            if (!kEarlySnap) {
-              // (split() ended on a barrier; the decision below is applied after the copy)
-              save_store(g_snap + (size_t)(j % P.nsnap) * 2 * P.vpad, true, false);
-              if (tid == 0) g_snap_tag[j % P.nsnap] = j;
-            }
+            // (split() ended on a barrier; the decision below is applied by the thread that waited for the copy engine)
+            save_store(g_snap + (size_t)(j % P.nsnap) * 2 * P.vpad, true, false);
+            if (tid == 0) g_snap_tag[j % P.nsnap] = j;
             if (ACT) {
               // the fixpoint has just converged: no moved bit, no dirty chunk; keep the entailment cache with the image
               const int fw = (T >> 5) * P.act_fpw / 4;
@@ -1431,19 +1400,16 @@ struct Ctx {
               for (int i = tid; i < fw; i += T) g[i] = ne[i];
             }
           }
-          if (!kEarlySnap || !pushed) {
-            if (tid == 0) {
-              if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
-              else {
-                Decision& d = dec[c.depth - 1];
-                d.cur = 0;
-                store.embed(d.var, d.clb0, d.cub0);
-                mark_var(d.var);
-                node_prologue();
-              }
+          if (tid == 0) {
+            if (!pushed) { c.leaf = 1; st->exhaustive = 0; }
+            else {
+              Decision& d = dec[c.depth - 1];
+              d.cur = 0;
+              store.embed(d.var, d.clb0, d.cub0);
+              mark_var(d.var);
             }
-            sync();
           }
+          sync();
         }
         // IV. backtrack: follow the rope, restore from the subproblem root, replay the decisions
         if (c.leaf) {
@@ -1481,7 +1447,6 @@ struct Ctx {
             store.embed(d.var, d.cur == 0 ? d.clb0 : d.clb1, d.cur == 0 ? d.cub0 : d.cub1);
             mark_var(d.var);
             c.cur_strategy = c.snap_strategy; c.next_unassigned = c.snap_next_unassigned;
-            node_prologue();
           }
           sync();
         }
