@@ -1967,12 +1967,15 @@ static tb_status configure(tb_solver* s) {
       set_error("cluster_size must be a power of two <= 16 whose slice fits in shared memory"); return TB_ERR_INVALID;
     }
   }
+  const bool shape_v1 = env_int("TB_SHAPE_V1", 0) != 0;      // round 1's placement and block shape, for A/B runs
   if (kind == TB_MEM_AUTO) {
-    // Prefer the propagator table in shared memory unless that leaves a single resident block where the store alone
-    // allows two: two half-size blocks hide each other's sweep barriers, which is worth more than the L2 stream costs
-    // (measured on the simplified trains15 network: 3.55 M nodes/s with 2 x 512 threads against 2.93 M with the table
-    // in shared memory and 1 x 1024, profiles/r01_placement_experiments.txt).
-    if (b_tcn >= 1 && !(b_tcn == 1 && b_store >= 2) && (b_tcn >= 4 || b_tcn * 2 >= std::min(b_store, 8))) kind = TB_MEM_TCN_SHARED;
+    // The store in shared memory whenever it fits, the table in tensor memory or L2: shared memory then holds more
+    // blocks, and independent blocks are what hides the barriers and the one-thread sections of the search (round 1
+    // already found 2 x 512 threads with the table in L2 faster than 1 x 1024 with the table in shared memory on
+    // trains15; with small single-warp blocks the same holds for the small networks - accap_a3: 42.4 M nodes/s with
+    // 24 x 32 threads per SM and the table in L2 against 27.6 M with 8 x 128 and the table in shared memory,
+    // profiles/r02_block_shapes.md). TCN_SHARED stays available on request.
+    if (shape_v1 && b_tcn >= 1 && !(b_tcn == 1 && b_store >= 2) && (b_tcn >= 4 || b_tcn * 2 >= std::min(b_store, 8))) kind = TB_MEM_TCN_SHARED;
     else if (b_store >= 1) kind = TB_MEM_STORE_SHARED;
     else if (cluster >= 2) kind = TB_MEM_STORE_CLUSTER;    // the store is larger than one SM: stripe it over DSMEM
     else kind = TB_MEM_GLOBAL;
@@ -2001,15 +2004,24 @@ static tb_status configure(tb_solver* s) {
   int bps = kind == TB_MEM_TCN_SHARED ? b_tcn : (kind == TB_MEM_STORE_SHARED ? b_store : 8);
   // Threads: keep ~1024 resident threads per SM at <= 64 registers (the reference compiles 256/block).
   int threads = s->opt.threads_per_block;
-  if (threads <= 0) {
-    // 1024 resident threads per SM (64 registers each), spread over as many blocks as shared memory allows, up to
-    // 8 x 128: small networks are bound by the barriers and the one-thread sections of the search, which more
-    // independent blocks overlap (accap_a3: 21.1 M nodes/s with 8 x 128 against 13.9 M with 4 x 256).
+  if (threads <= 0 && shape_v1) {
+    // (round 1: 1024 resident threads per SM spread over up to 8 blocks)
     bps = std::min(bps, 8);
     threads = bps >= 8 ? 128 : (bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024));
     threads = std::min(threads, TB_MAX_THREADS);
-    // do not use more threads than there is work per sweep
     while (threads > 128 && threads / 2 >= s->P.nchunks * 32) threads /= 2;   // at least one chunk per warp
+  } else if (threads <= 0) {
+    // As many blocks as shared memory holds (up to 32 per SM), each with as FEW warps as keeps (a) about 24 warps
+    // resident per SM and (b) a warp's share of a sweep around 24 chunks or more: a sweep costs every warp some 300
+    // instructions of class entry / exit and flag handling whatever it visits, and every block-wide barrier waits
+    // for the slowest warp, so few long warps beat many short ones - down to single-warp blocks, whose barriers are
+    // free (accap_a3, 40 chunks: 24 x 32 threads per SM; trains15, 440 chunks, 2 blocks fit: 2 x 512; wordpress: 1 x 1024).
+    bps = std::min(bps, 32);
+    int warps = 1;
+    while (warps < 32 && warps * bps < 24) warps *= 2;
+    while (warps < 32 && warps * 2 * 24 <= s->P.nchunks) warps *= 2;
+    threads = std::min(32 * warps, TB_MAX_THREADS);
+    bps = std::max(1, std::min(bps, 1024 / threads));                          // 64 registers per thread
   }
   threads = pow2_threads(threads);
   bps = std::max(1, std::min(bps, 2048 / threads));
