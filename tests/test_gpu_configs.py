@@ -48,12 +48,16 @@ def load(name):
 @pytest.mark.parametrize("name,kind", [("simplified:example_wordpress7_500", abi.MEM_STORE_SHARED),
                                        ("example_wordpress7_500", abi.MEM_STORE_CLUSTER),
                                        ("simplified:trains15", abi.MEM_STORE_SHARED),
-                                       ("simplified:accap_a3", abi.MEM_TCN_SHARED)])
+                                       ("simplified:accap_a3", abi.MEM_STORE_SHARED),
+                                       ("simplified:accap_a3", -abi.MEM_TCN_SHARED)])
 def test_dive_subproblems_bit_exact_on_the_headline_networks(eng, orc, name, kind):
     pb, _ = load(name)
     depth = 5
-    with eng.Solver(pb) as s:
-        assert s.config()["mem_kind"] == kind          # the placement policy's own choice
+    # (a negative kind is requested explicitly: the table in shared memory is no longer anybody's automatic choice)
+    with (eng.Solver(pb) if kind >= 0 else eng.Solver(pb, mem_kind=-kind)) as s:
+        assert s.config()["mem_kind"] == abs(kind)          # the placement policy's own choice
+        if name == "simplified:accap_a3" and kind >= 0:
+            assert s.config()["threads_per_block"] == 32   # single-warp blocks, as many as shared memory holds
         g = s.dive_batch(0, 1 << depth, depth)
     for idx in range(1 << depth):
         o = orc.dive(pb, idx, depth)

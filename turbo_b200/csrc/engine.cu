@@ -2004,8 +2004,11 @@ static tb_status configure(tb_solver* s) {
   int bps = kind == TB_MEM_TCN_SHARED ? b_tcn : (kind == TB_MEM_STORE_SHARED ? b_store : 8);
   // Threads: keep ~1024 resident threads per SM at <= 64 registers (the reference compiles 256/block).
   int threads = s->opt.threads_per_block;
-  if (threads <= 0 && shape_v1) {
-    // (round 1: 1024 resident threads per SM spread over up to 8 blocks)
+  if (threads <= 0 && (shape_v1 || s->P.nchunks < 16)) {
+    // Round 1's shape: 1024 resident threads per SM spread over up to 8 blocks. Still the choice for the tiniest
+    // networks (under 16 chunks, i.e. 500 propagators): their nodes are all search bookkeeping, and 32 single-warp
+    // blocks per SM, each somewhere else in a 150 KB kernel, run it 2-3 x slower than 8 blocks of 4 warps (pat1, pat10,
+    // pat11: profiles/r02_block_shapes.md).
     bps = std::min(bps, 8);
     threads = bps >= 8 ? 128 : (bps >= 4 ? 256 : (bps >= 2 ? 512 : 1024));
     threads = std::min(threads, TB_MAX_THREADS);
@@ -2387,7 +2390,11 @@ extern "C" tb_status tb_create(tb_solver** out, const tb_problem* pb, const tb_o
   int d = opt.subproblems_power;
   if (d < 0) {
     d = 0;
-    const unsigned long long want = (unsigned long long)opt.subproblems_factor * (unsigned long long)s->num_blocks * (unsigned long long)opt.gpu_world;
+    // (per block up to 4 blocks per SM: the single-warp blocks of the small networks come 24 to an SM, and a dive per
+    // subproblem is what a small search tree then mostly consists of - pat10: 30 M nodes for 2^21 subproblems, 7.5 M for
+    // 2^19; the blocks that run out of subproblems split the ones that are left, see tail splitting)
+    const unsigned long long per_gpu = (unsigned long long)std::min(s->num_blocks, 4 * s->num_sms);
+    const unsigned long long want = (unsigned long long)opt.subproblems_factor * per_gpu * (unsigned long long)opt.gpu_world;
     while ((1ull << d) < want && d < 62) ++d;
   }
   pt.mark("streams, L2 window");
