@@ -386,14 +386,19 @@ struct Ctx {
       SplitEntry* e = pool + i;
       const unsigned cnt = *(volatile unsigned*)&e->count;
       if (cnt == 0) { first_open = min(first_open, i); continue; }            // being written
-      if (*(volatile unsigned*)&e->next >= cnt) continue;
+      unsigned long long v = *(volatile unsigned long long*)&e->next;
+      if ((unsigned)v >= cnt) continue;
       first_open = min(first_open, i);
-      if (*(volatile unsigned*)&e->epoch != P.epoch) continue;
-      const unsigned j = src < 0 ? atomicAdd(&e->next, 1u) : atomicAdd_system(&e->next, 1u);
-      if (j < cnt) {
-        c.task_idx = e->base + (unsigned long long)j; c.task_depth = e->depth; c.task_entry = (int)i; c.task_j = j; c.task_src = src;
-        c.have_task = 1;
-        return true;
+      // (a CAS, as on the peers' dispensers: the counter of another run is never advanced)
+      while ((unsigned)(v >> 32) == P.epoch && (unsigned)v < cnt) {
+        const unsigned long long old = src < 0 ? atomicCAS(&e->next, v, v + 1ull) : atomicCAS_system(&e->next, v, v + 1ull);
+        if (old == v) {
+          const unsigned j = (unsigned)v;
+          c.task_idx = e->base + (unsigned long long)j; c.task_depth = e->depth; c.task_entry = (int)i; c.task_j = j; c.task_src = src;
+          c.have_task = 1;
+          return true;
+        }
+        v = old;
       }
     }
     if (first_open > *(volatile unsigned*)(ctl + TB_SPLIT_HINT)) {
@@ -436,7 +441,7 @@ struct Ctx {
     const unsigned i = atomicAdd(P.split_ctl + TB_SPLIT_N, 1u);
     if (i >= (unsigned)TB_SPLIT_CAP) return false;
     SplitEntry* e = P.split_pool + i;
-    e->base = c.task_idx << P.split_bits; e->depth = c.task_depth + P.split_bits; e->next = 0u; e->epoch = P.epoch;
+    e->base = c.task_idx << P.split_bits; e->depth = c.task_depth + P.split_bits; e->next = (unsigned long long)P.epoch << 32; e->epoch = P.epoch;
     __threadfence_system();
     *(volatile unsigned*)&e->count = 1u << P.split_bits;
     if (c.task_entry < 0) st->eps_split += 1;      // (a child that is split again is counted with neither)
@@ -1302,7 +1307,16 @@ struct Ctx {
           if (tid == 0 && c.task_entry >= 0) {
             // a child of a split subproblem: its siblings below the same leaf need no dive either
             SplitEntry* e = split_pool_of(c.task_src < 0 ? P.cells : P.peer_cells[c.task_src]) + c.task_entry;
-            if (remaining < 31) atomicMax_system(&e->next, min(e->count, ((c.task_j >> remaining) + 1u) << remaining));
+            if (remaining < 31) {
+              // (the entry's epoch is in the high half of the word: a max can only move this run's counter)
+              const unsigned long long to = ((unsigned long long)P.epoch << 32) | min(e->count, ((c.task_j >> remaining) + 1u) << remaining);
+              unsigned long long v = *(volatile unsigned long long*)&e->next;
+              while ((unsigned)(v >> 32) == P.epoch && v < to) {
+                const unsigned long long old = atomicCAS_system(&e->next, v, to);
+                if (old == v) break;
+                v = old;
+              }
+            }
           } else if (tid == 0) {
             // nobody needs to dive into [idx, next) any more: advance every shard's dispenser past it
             const unsigned long long next = ((idx >> remaining) + 1ull) << remaining;

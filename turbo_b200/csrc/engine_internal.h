@@ -63,10 +63,12 @@ struct SplitEntry {
   unsigned long long base;      // index of the first child at depth `depth`
   int depth;                    // dive depth of the children
   unsigned count;               // number of children (0 = entry not published yet)
-  unsigned next;                // dispenser over the children (fetch-add; monotone max on a failed subtree)
-  unsigned epoch;               // the run the entry belongs to (a peer of another run leaves it alone)
-  unsigned pad_[2];
+  unsigned long long next;      // dispenser over the children, (epoch << 32) | next child: advanced by CAS only, so that
+                                // a block of another run of a linked solver can never hand out or skip this run's children
+  unsigned epoch;               // the run the entry belongs to
+  unsigned pad_;
 };
+static_assert(sizeof(SplitEntry) == 32, "TB_CELL_BLOCK_BYTES counts 32 bytes per pool entry");
 #define TB_SPLIT_CAP 16384
 // words of the split control block (unsigned), which lives in the cell block (TB_CELL_SPLIT) so that the peers see it
 enum { TB_SPLIT_N = 0, TB_SPLIT_WAITING = 1, TB_SPLIT_GONE = 2, TB_SPLIT_HINT = 3, TB_SPLIT_STARTED = 4, TB_SPLIT_NSLOTS = 5, TB_SPLIT_EPOCH = 6 };
