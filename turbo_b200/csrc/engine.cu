@@ -424,13 +424,15 @@ struct Ctx {
     return false;
   }
   // Every block of every linked GPU (of this run) is waiting or gone: the search is over. A peer whose control block
-  // carries another epoch has not started this run yet (or never will): during `grace` it counts as busy.
+  // carries an OLDER epoch has not started this run yet - linked solvers make the same sequence of tb_solve calls, so it
+  // will: during `grace` it counts as busy. One with a newer epoch has left this run behind.
   __device__ __forceinline__ bool everybody_idle(bool grace) const {
     if (*(volatile unsigned*)(P.split_ctl + TB_SPLIT_WAITING) + *(volatile unsigned*)(P.split_ctl + TB_SPLIT_GONE) < (unsigned)nslots) return false;
     if (P.share_split)
       for (int g = 0; g < P.npeers; ++g) {
         volatile unsigned* ctl = split_ctl_of(P.peer_cells[g]);
-        if (ctl[TB_SPLIT_EPOCH] != P.epoch) { if (grace) return false; continue; }
+        const unsigned pe = ctl[TB_SPLIT_EPOCH];
+        if (pe != P.epoch) { if (grace && pe < P.epoch) return false; continue; }
         if (ctl[TB_SPLIT_WAITING] + ctl[TB_SPLIT_GONE] < ctl[TB_SPLIT_NSLOTS]) return false;
       }
     return true;
@@ -489,7 +491,8 @@ struct Ctx {
       if (stop_raised()) return;
       const bool far = (it & 7u) == 0u;
       if (take_split(far)) { atomicSub(P.split_ctl + TB_SPLIT_WAITING, 1u); c.counted_idle = 0; return; }
-      if ((far || !P.share_split) && everybody_idle(globaltimer_ns() - t0 < 20000000ull)) return;
+      // (grace: one second for a peer whose host has not launched this run yet - first-run allocations, process skew)
+      if ((far || !P.share_split) && everybody_idle(globaltimer_ns() - t0 < 1000000000ull)) return;
       __nanosleep(2000);
     }
   }
