@@ -270,3 +270,25 @@ def test_tail_splitting_keeps_status_and_optimum(eng, name, monkeypatch):
         h = s.solve()
     assert h["exhaustive"] and golden_io.user_objective(info, h["lb"], h["ub"]) == info["expected"]
     assert h["stats"]["eps_split_subproblems"] == 0
+
+
+# ---- automatic placement and block shape (profiles/r02_block_shapes.md) ---------------------------------------
+
+def test_automatic_placement_and_block_shape(eng, monkeypatch):
+    """The store in shared memory whenever it fits, as many few-warp blocks as fit: single-warp blocks for accap_a3,
+    2 x 512 threads per SM for trains15, 1 x 1024 for wordpress7_500; TB_SHAPE_V1=1 brings back round 1's 8 x 128 with the
+    table in shared memory. The default number of subproblems counts at most 4 blocks per SM."""
+    def shape(name, **kw):
+        pb, _ = load(name)
+        with eng.Solver(pb, subproblems_power=-1, **kw) as s:
+            c = s.config()
+        return c["mem_kind"], c["threads_per_block"], c["blocks_per_sm"], c["num_blocks"], c["subproblems_power"]
+
+    kind, threads, bps, blocks, power = shape("simplified:accap_a3")
+    assert (kind, threads) == (abi.MEM_STORE_SHARED, 32) and bps >= 20
+    assert (1 << power) >= 300 * min(blocks, 4 * (blocks // bps)) > (1 << (power - 1))
+    assert shape("simplified:trains15")[:3] == (abi.MEM_STORE_SHARED, 512, 2)
+    assert shape("simplified:example_wordpress7_500")[:3] == (abi.MEM_STORE_SHARED, 1024, 1)
+    assert shape("simplified:accap_a3", mem_kind=abi.MEM_TCN_SHARED)[0] == abi.MEM_TCN_SHARED
+    monkeypatch.setenv("TB_SHAPE_V1", "1")
+    assert shape("simplified:accap_a3")[:3] == (abi.MEM_TCN_SHARED, 128, 8)
